@@ -1,0 +1,177 @@
+/*
+ * rgbdgan_b200.h -- C-ABI of librgbdgan_b200.so: the B200 (sm_100a) implementation of
+ * RGBD-GAN's 3D-consistency hot path.
+ *
+ * The reference (nogu-atsu/RGBD-GAN) is pure Python: it has no FFI/plugin layer.  Its
+ * boundary for this path is the Python call surface of common/loss_functions.py
+ * (LossFuncRotate, warp, inv_warp, bilinear) and deepvoxel/projection.py +
+ * deepvoxel/deepvoxel.py::interpolate_trilinear.  These entry points are what a
+ * Chainer FunctionNode (or any other host binding: ctypes, CuPy, torch) calls in place
+ * of the chain of Chainer/CuPy kernels the reference launches; each one cites the
+ * reference lines it replaces.  INTEGRATION.md shows the reference-side stubs.
+ *
+ * Conventions
+ *   - every pointer is a CALLER-OWNED DEVICE pointer (cupy `arr.data.ptr`, torch
+ *     `tensor.data_ptr()`), fp32, C-contiguous, 16-byte aligned; the library never
+ *     allocates device memory and keeps no global mutable state
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); every call
+ *     is asynchronous on that stream and performs no host synchronisation, except
+ *     rgbd_dv_compute_proj_idcs, whose result size is data dependent (as in the reference)
+ *   - return value: 0 on success; > 0 a cudaError_t from a launch; < 0 an argument error
+ *     (RGBD_E_*); rgbd_last_error() gives a thread-local message.  No exceptions, no prints
+ *   - images are (B,C,H,W) NCHW with the depth in channel C-1; gradients have the
+ *     same layout and are OVERWRITTEN (Chainer accumulates outside the node)
+ *   - `workspace` is scratch for the duration of the call on `stream`, sized by the
+ *     matching *_workspace_bytes(); contents are undefined afterwards
+ *   - B is the number of PAIRS held by this process; `n_pairs_global` is the number of
+ *     pairs the reference's means run over (== B unless the batch is sharded over GPUs),
+ *     so per-shard results just add up (loss parts) or need no communication (gradients)
+ */
+#ifndef RGBDGAN_B200_H
+#define RGBDGAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RGBD_B200_VERSION 100
+
+#if defined(__GNUC__)
+#define RGBD_API __attribute__((visibility("default")))
+#else
+#define RGBD_API
+#endif
+
+#define RGBD_E_ARG (-1)        /* null pointer / non-positive size / bad enum        */
+#define RGBD_E_ALIGN (-2)      /* pointer not 16-byte aligned                        */
+#define RGBD_E_WORKSPACE (-3)  /* workspace missing or too small                     */
+#define RGBD_E_UNSUPPORTED (-4)
+
+#define RGBD_NORM_L1 1 /* F.mean_absolute_error (loss_functions.py:137-138) */
+#define RGBD_NORM_L2 2 /* F.mean_squared_error  (loss_functions.py:139-140) */
+
+RGBD_API int rgbd_version(void);
+RGBD_API const char *rgbd_last_error(void);
+
+/* Options of LossFuncRotate.__call__ (common/loss_functions.py:63-64) + __init__ (:32-37). */
+typedef struct {
+    int norm;             /* RGBD_NORM_L1 | RGBD_NORM_L2                                  */
+    int occlusion_aware;  /* :112-119                                                     */
+    float max_depth;      /* :121-127, NaN = None                                         */
+    float min_depth;      /* :129-135, NaN = None                                         */
+    float lambda_geometric; /* :143-144 (only used by backward entry points)              */
+    long long n_pairs_global; /* denominator pairs; 0 means "= B"                         */
+} rgbd_loss_opts;
+
+/* ---- LossFuncRotate.__call__ : common/loss_functions.py:63-146 (+ warp :171-175,
+ *      inv_warp :178-182, bilinear :185-228 fused) ---------------------------------------
+ * Pose inputs are the constant factors the reference computes with raw xp.matmul
+ * (:89-91,:174,:181); the host wrapper computes them with the same NumPy sequence:
+ *   M  (B,9) = K R K^-1        c  (B,3) = (K R) t     direction img -> img_rot (c is subtracted)
+ *   Mi (B,9) = K R^T K^-1      ci (B,3) = -(K t)      direction img_rot -> img (ci is subtracted)
+ */
+
+RGBD_API size_t rgbd_consistency_workspace_bytes(int B, int C, int H, int W);
+
+/* Forward only.  loss_parts (device, 8 floats): [0..3] = the four means of :141-144 restricted
+ * to these B pairs, in the order {rgb, rgb_rot, depth, depth_rot}; [4] = the loss combined as
+ * :141-144 does, (p0+p1) + (p2*lambda + p3*lambda), valid as is when the batch is not sharded
+ * (sharded: all-reduce [0..3] and recombine); [5..7] = 0, reserved.
+ * new_zp  (nullable): (2B,HW,3), the second return value of __call__ (:146).
+ * masks   (nullable): (2,2B,HW) uint8 debug planes: [0] = not_getting_out (:215-216),
+ *                     [1] = not_occluded (:114-115; 1 when occlusion_aware == 0).          */
+RGBD_API int rgbd_consistency_fwd(const float *img, const float *img_rot, const float *M, const float *c,
+                         const float *Mi, const float *ci, int B, int C, int H, int W,
+                         const rgbd_loss_opts *opts, float *loss_parts, float *new_zp,
+                         uint8_t *masks, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Backward by recomputation, for an arbitrary upstream gradient of the loss (what Chainer's
+ * autograd does for `loss_gen.backward()`, updater.py:387).  The upstream gradient is
+ * gy * (*gy_dev): gy_dev (nullable) is a DEVICE scalar, so a FunctionNode can hand over the
+ * gradient array it was given without a device->host read.  g_new_zp (nullable, (2B,HW,3)) is
+ * the upstream gradient of the second output.  g_img / g_img_rot are overwritten.            */
+RGBD_API int rgbd_consistency_bwd(const float *img, const float *img_rot, const float *M, const float *c,
+                         const float *Mi, const float *ci, int B, int C, int H, int W,
+                         const rgbd_loss_opts *opts, float gy, const float *gy_dev,
+                         const float *g_new_zp, float *g_img, float *g_img_rot, void *workspace,
+                         size_t workspace_bytes, void *stream);
+
+/* Forward + backward in one pass for an upstream gradient known in advance (in the
+ * reference's training loop gy is the constant lambda_rotate, updater.py:363-365):
+ * same outputs as rgbd_consistency_fwd followed by rgbd_consistency_bwd(gy); new_zp nullable. */
+RGBD_API int rgbd_consistency_fwd_bwd(const float *img, const float *img_rot, const float *M, const float *c,
+                             const float *Mi, const float *ci, int B, int C, int H, int W,
+                             const rgbd_loss_opts *opts, float gy, float *loss_parts,
+                             float *new_zp, float *g_img, float *g_img_rot, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
+/* Companion of rgbd_consistency_fwd_bwd for autograd bindings: when the upstream gradient
+ * that finally arrives (*gy_dev) differs from gy_expected, multiply both stashed gradients by
+ * (*gy_dev / gy_expected) in place; when it is equal (the normal case) the kernel exits
+ * without touching memory.  n_elems = elements per gradient tensor (multiple of 4).        */
+RGBD_API int rgbd_consistency_rescale(float *g_img, float *g_img_rot, size_t n_elems, const float *gy_dev,
+                             float gy_expected, void *stream);
+
+/* ---- free functions of common/loss_functions.py ------------------------------------------ */
+
+/* warp (:171-175) / inv_warp (:178-182): new_zp[b,n,:] = M[b] (z[b,n] * p[:,n]) - cv[b]
+ * with p = (col,row,1) (:59-61).  z: (B,HW); new_zp: (B,HW,3).  inv_warp passes cv = -(K t). */
+RGBD_API int rgbd_warp_fwd(const float *z, const float *M, const float *cv, int B, int H, int W,
+                  float *new_zp, void *stream);
+/* g_z (B,HW) = sum_k (M[b]^T g_new_zp[b,n,:])_k p_k[n]   (autograd of F.matmul and z * p) */
+RGBD_API int rgbd_warp_bwd(const float *g_new_zp, const float *M, int B, int H, int W, float *g_z,
+                  void *stream);
+
+/* bilinear(img, zp) (:185-228): warped (B*HW,C), mask (B*HW) uint8 = not_getting_out */
+RGBD_API int rgbd_bilinear_fwd(const float *img, const float *zp, int B, int C, int H, int W,
+                      float *warped, uint8_t *mask, void *stream);
+/* autograd of bilinear: g_img (B,C,H,W) and g_zp (B,HW,3), both overwritten */
+RGBD_API int rgbd_bilinear_bwd(const float *img, const float *zp, const float *g_warped, int B, int C,
+                      int H, int W, float *g_img, float *g_zp, void *stream);
+
+/* ---- DeepVoxels projection: deepvoxel/projection.py:48-105 and
+ *      deepvoxel/deepvoxel.py:388-428 ------------------------------------------------------- */
+
+typedef struct {
+    int W, H, D;           /* projection_image_dims[0], [1]; frustrum_depth (projection.py:56)   */
+    int G;                 /* grid_dims (cubic)                                                */
+    float fx, fy, cx, cy;  /* projection_intrinsic[0][0], [1][1], [0][2], [1][2] (:78-79)        */
+    float voxel_size;      /* :73,:87                                                          */
+    float near_plane;      /* :74 (fp32, as on the reference's NumPy-1.x / CuPy)               */
+} rgbd_dv_params;
+
+/* ProjectionHelper.compute_proj_idcs for one camera: writes the kept frustum indices in
+ * ascending order to lin_ind (capacity W*H*D int32) and their voxel coordinates to
+ * voxel_coords (3 rows with row stride W*H*D).  *M_host receives the count (0 is the
+ * reference's `None`).  Synchronises `stream` (the count sizes the caller's arrays, like
+ * the reference's host-side `.any()` / boolean indexing, :98-103).  workspace: at least
+ * rgbd_dv_workspace_bytes(p).                                                               */
+RGBD_API size_t rgbd_dv_workspace_bytes(const rgbd_dv_params *p);
+RGBD_API int rgbd_dv_compute_proj_idcs(const rgbd_dv_params *p, const float *cam2world, int32_t *lin_ind,
+                              float *voxel_coords, int *M_host, void *workspace,
+                              size_t workspace_bytes, void *stream);
+
+/* interpolate_trilinear (deepvoxel.py:388-428) for ONE sample from explicit index lists:
+ * grid (F,G,G,G) -> frustum (F,D,H,W), zero where not listed.  ld = row stride of voxel_coords. */
+RGBD_API int rgbd_dv_trilinear_fwd(const float *grid, const int32_t *lin_ind, const float *voxel_coords,
+                          int ld, int M, int F, const rgbd_dv_params *p, float *frustum, void *stream);
+/* its autograd (the "lift" direction): g_frustum (F,D,H,W) -> g_grid (F,G,G,G), overwritten */
+RGBD_API int rgbd_dv_trilinear_bwd(const float *g_frustum, const int32_t *lin_ind, const float *voxel_coords,
+                          int ld, int M, int F, const rgbd_dv_params *p, float *g_grid, void *stream);
+
+/* Fused batch path used by the generator forward (deepvoxels_generator.py:287-299 ->
+ * deepvoxel.py:879-884): compute_proj_idcs + interpolate_trilinear per sample without the
+ * index lists, the compaction or the host sync.  grid (B,F,G,G,G), cam2world (B,16),
+ * frustum (B,F,D,H,W).                                                                     */
+RGBD_API int rgbd_dv_project_fwd(const rgbd_dv_params *p, const float *grid, const float *cam2world, int B,
+                        int F, float *frustum, void *stream);
+RGBD_API int rgbd_dv_project_bwd(const rgbd_dv_params *p, const float *g_frustum, const float *cam2world,
+                        int B, int F, float *g_grid, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGBDGAN_B200_H */

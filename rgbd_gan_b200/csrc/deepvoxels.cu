@@ -1,0 +1,347 @@
+// deepvoxels.cu -- DeepVoxels frustum <-> voxel-grid projection sampling:
+//   ProjectionHelper.compute_proj_idcs  (deepvoxel/projection.py:48-105)
+//   interpolate_trilinear + its autograd (deepvoxel/deepvoxel.py:388-428)
+// Per-element recipe: SURVEY.md Appendix A2 (fp32-pinned scalar semantics, quirks Q5-Q8, Q10).
+#include "common.cuh"
+
+namespace rgbd {
+
+struct Cam { float t[12]; };   // rows 0..2 of cam2world (row 3 is not needed: voxel_coords = grid_coords[:3])
+
+__device__ __forceinline__ Cam load_cam(const float *__restrict__ cam2world)
+{
+    Cam c;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) c.t[k] = __ldg(cam2world + k);
+    return c;
+}
+
+// voxel coordinates of frustum element l; returns the in-bounds flag (projection.py:64-96)
+__device__ __forceinline__ bool dv_coords(const rgbd_dv_params &P, const Cam &T, int l, float vc[3])
+{
+    const int WH = P.W * P.H;
+    const int d = l / WH;                                             // :64
+    const int tmp = l - d * WH;                                       // :65-66
+    const float yrow = (float)((double)tmp / (double)P.W);            // :67 true division (fractional row, Q5)
+    const float xcol = (float)(tmp % P.W);                            // :68
+    float zc = __fmul_rn((float)d, P.voxel_size);                     // :73
+    zc = __fadd_rn(zc, P.near_plane);                                 // :74 (fp32, Q6)
+    float xc = __fdiv_rn(__fsub_rn(xcol, P.cx), P.fx);                // :78
+    float yc = __fdiv_rn(__fsub_rn(yrow, P.cy), P.fy);                // :79
+    xc = __fmul_rn(xc, zc);                                           // :80
+    yc = __fmul_rn(yc, zc);
+    bool keep = true;
+    const float half = (float)P.G / 2.0f, Gf = (float)P.G;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {                                     // xp.dot (sgemm, K=4): fma chain  :82
+        float g = __fmul_rn(T.t[4 * r], xc);
+        g = __fmaf_rn(T.t[4 * r + 1], yc, g);
+        g = __fmaf_rn(T.t[4 * r + 2], zc, g);
+        g = __fmaf_rn(T.t[4 * r + 3], 1.0f, g);
+        const float v = __fadd_rn(__fdiv_rn(g, P.voxel_size), half);  // :87-88
+        vc[r] = v;
+        keep = keep && (v >= 0.0f) && (v < Gf);                       // :92-96
+    }
+    return keep;
+}
+
+struct Taps {
+    int off[8];         // element offsets into one (G,G,G) feature brick, corner order of deepvoxel.py:416-423
+    float ax[8], ay[8], az[8];
+};
+
+// deepvoxel.py:394-412: axis swap (grid axis 2 <- vc[2], axis 4 <- vc[0]), truncation, clamp, fp64 fractions
+__device__ __forceinline__ void dv_taps(const float vc[3], int G, Taps &t)
+{
+    const float X = vc[2], Y = vc[1], Z = vc[0];
+    const int x0 = __float2int_rz(X), y0 = __float2int_rz(Y), z0 = __float2int_rz(Z);
+    const int x1 = min(max(x0 + 1, 0), G - 1), y1 = min(max(y0 + 1, 0), G - 1), z1 = min(max(z0 + 1, 0), G - 1);
+    const double fx = (double)X - (double)x0, fy = (double)Y - (double)y0, fz = (double)Z - (double)z0;
+    const float wx1 = (float)fx, wx0 = (float)(1.0 - fx);
+    const float wy1 = (float)fy, wy0 = (float)(1.0 - fy);
+    const float wz1 = (float)fz, wz0 = (float)(1.0 - fz);
+    const int xs[2] = {x0, x1}, ys[2] = {y0, y1}, zs[2] = {z0, z1};
+    const float wxs[2] = {wx0, wx1}, wys[2] = {wy0, wy1}, wzs[2] = {wz0, wz1};
+    // corner order: (0,0,0)(1,0,0)(0,1,0)(0,0,1)(1,0,1)(0,1,1)(1,1,0)(1,1,1)
+    const int ox[8] = {0, 1, 0, 0, 1, 0, 1, 1}, oy[8] = {0, 0, 1, 0, 0, 1, 1, 1}, oz[8] = {0, 0, 0, 1, 1, 1, 0, 1};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        t.off[k] = (xs[ox[k]] * G + ys[oy[k]]) * G + zs[oz[k]];
+        t.ax[k] = wxs[ox[k]]; t.ay[k] = wys[oy[k]]; t.az[k] = wzs[oz[k]];
+    }
+}
+
+__device__ __forceinline__ float dv_interp(const float *__restrict__ brick, const Taps &t)
+{
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float term = __fmul_rn(__fmul_rn(__fmul_rn(__ldg(brick + t.off[k]), t.ax[k]), t.ay[k]), t.az[k]);
+        acc = (k == 0) ? term : __fadd_rn(acc, term);
+    }
+    return acc;
+}
+
+// ---------------------------------------------------------------- fused batch path (no index lists)
+__global__ void __launch_bounds__(kThreads)
+k_dv_project_fwd(const rgbd_dv_params P, const float *__restrict__ grid, const float *__restrict__ cam2world,
+                 int F, float *__restrict__ frustum)
+{
+    const int n = P.W * P.H * P.D;
+    const int l = blockIdx.x * kThreads + threadIdx.x;
+    const int b = blockIdx.y;
+    if (l >= n) return;
+    const Cam T = load_cam(cam2world + 16 * b);
+    float vc[3];
+    const bool keep = dv_coords(P, T, l, vc);
+    const size_t G3 = (size_t)P.G * P.G * P.G;
+    float *out = frustum + (size_t)b * F * n + l;
+    if (!keep) {
+        for (int f = 0; f < F; ++f) out[(size_t)f * n] = 0.0f;
+        return;
+    }
+    Taps t;
+    dv_taps(vc, P.G, t);
+    const float *g = grid + (size_t)b * F * G3;
+    for (int f = 0; f < F; ++f) out[(size_t)f * n] = dv_interp(g + (size_t)f * G3, t);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_dv_project_bwd(const rgbd_dv_params P, const float *__restrict__ g_frustum, const float *__restrict__ cam2world,
+                 int F, float *__restrict__ g_grid)
+{
+    const int n = P.W * P.H * P.D;
+    const int l = blockIdx.x * kThreads + threadIdx.x;
+    const int b = blockIdx.y;
+    if (l >= n) return;
+    const Cam T = load_cam(cam2world + 16 * b);
+    float vc[3];
+    if (!dv_coords(P, T, l, vc)) return;
+    Taps t;
+    dv_taps(vc, P.G, t);
+    const size_t G3 = (size_t)P.G * P.G * P.G;
+    const float *go = g_frustum + (size_t)b * F * n + l;
+    float *gg = g_grid + (size_t)b * F * G3;
+    for (int f = 0; f < F; ++f) {
+        const float g = __ldg(go + (size_t)f * n);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            atomicAdd(gg + (size_t)f * G3 + t.off[k], ((g * t.az[k]) * t.ay[k]) * t.ax[k]);
+    }
+}
+
+// ---------------------------------------------------------------- explicit index-list path
+__global__ void __launch_bounds__(kThreads)
+k_dv_trilinear_fwd(const float *__restrict__ grid, const int32_t *__restrict__ lin_ind,
+                   const float *__restrict__ voxel_coords, int ld, int M, int F, int G, int n,
+                   float *__restrict__ frustum)
+{
+    const int m = blockIdx.x * kThreads + threadIdx.x;
+    if (m >= M) return;
+    const float vc[3] = {voxel_coords[m], voxel_coords[ld + m], voxel_coords[2 * (size_t)ld + m]};
+    Taps t;
+    dv_taps(vc, G, t);
+    const size_t G3 = (size_t)G * G * G;
+    float *out = frustum + lin_ind[m];
+    for (int f = 0; f < F; ++f) out[(size_t)f * n] = dv_interp(grid + (size_t)f * G3, t);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_dv_trilinear_bwd(const float *__restrict__ g_frustum, const int32_t *__restrict__ lin_ind,
+                   const float *__restrict__ voxel_coords, int ld, int M, int F, int G, int n,
+                   float *__restrict__ g_grid)
+{
+    const int m = blockIdx.x * kThreads + threadIdx.x;
+    if (m >= M) return;
+    const float vc[3] = {voxel_coords[m], voxel_coords[ld + m], voxel_coords[2 * (size_t)ld + m]};
+    Taps t;
+    dv_taps(vc, G, t);
+    const size_t G3 = (size_t)G * G * G;
+    const float *go = g_frustum + lin_ind[m];
+    for (int f = 0; f < F; ++f) {
+        const float g = __ldg(go + (size_t)f * n);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            atomicAdd(g_grid + (size_t)f * G3 + t.off[k], ((g * t.az[k]) * t.ay[k]) * t.ax[k]);
+    }
+}
+
+// ---------------------------------------------------------------- compute_proj_idcs (ordered compaction)
+__global__ void __launch_bounds__(kThreads)
+k_dv_count(const rgbd_dv_params P, const float *__restrict__ cam2world, int *__restrict__ block_counts)
+{
+    const int n = P.W * P.H * P.D;
+    const int l = blockIdx.x * kThreads + threadIdx.x;
+    const Cam T = load_cam(cam2world);
+    float vc[3];
+    const bool keep = (l < n) && dv_coords(P, T, l, vc);
+    const int cnt = __syncthreads_count(keep);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = cnt;
+}
+
+// exclusive scan of the block counts by one block (nblocks is a few thousand at most)
+__global__ void __launch_bounds__(1024)
+k_dv_scan(const int *__restrict__ block_counts, int nblocks, int *__restrict__ block_offsets, int *__restrict__ total)
+{
+    __shared__ int sh[1024];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int idx = base + threadIdx.x;
+        const int v = idx < nblocks ? block_counts[idx] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int s = 1; s < 1024; s <<= 1) {                         // Hillis-Steele inclusive scan
+            const int add = threadIdx.x >= s ? sh[threadIdx.x - s] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (idx < nblocks) block_offsets[idx] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_dv_compact(const rgbd_dv_params P, const float *__restrict__ cam2world, const int *__restrict__ block_offsets,
+             int32_t *__restrict__ lin_ind, float *__restrict__ voxel_coords, int ld)
+{
+    __shared__ int warp_base[kThreads / 32];
+    const int n = P.W * P.H * P.D;
+    const int l = blockIdx.x * kThreads + threadIdx.x;
+    const Cam T = load_cam(cam2world);
+    float vc[3];
+    const bool keep = (l < n) && dv_coords(P, T, l, vc);
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_base[wid] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int w = 0; w < kThreads / 32; ++w) { const int v = warp_base[w]; warp_base[w] = acc; acc += v; }
+    }
+    __syncthreads();
+    if (keep) {
+        const int pos = block_offsets[blockIdx.x] + warp_base[wid] + __popc(bal & ((1u << lane) - 1u));
+        lin_ind[pos] = l;
+        voxel_coords[pos] = vc[0];
+        voxel_coords[(size_t)ld + pos] = vc[1];
+        voxel_coords[2 * (size_t)ld + pos] = vc[2];
+    }
+}
+
+static bool dv_ok(const rgbd_dv_params *p)
+{
+    return p && p->W > 0 && p->H > 0 && p->D > 0 && p->G > 1 && p->voxel_size > 0.0f && p->fx != 0.0f && p->fy != 0.0f;
+}
+
+}  // namespace rgbd
+
+using namespace rgbd;
+
+extern "C" {
+
+RGBD_API size_t rgbd_dv_workspace_bytes(const rgbd_dv_params *p)
+{
+    if (!dv_ok(p)) return 0;
+    const size_t nblocks = ((size_t)p->W * p->H * p->D + kThreads - 1) / kThreads;
+    return (2 * nblocks + 64) * sizeof(int);
+}
+
+RGBD_API int rgbd_dv_compute_proj_idcs(const rgbd_dv_params *p, const float *cam2world, int32_t *lin_ind,
+                              float *voxel_coords, int *M_host, void *workspace, size_t workspace_bytes,
+                              void *stream)
+{
+    if (!dv_ok(p) || !cam2world || !lin_ind || !voxel_coords || !M_host) {
+        set_error("rgbd_dv_compute_proj_idcs: null pointer or bad params");
+        return RGBD_E_ARG;
+    }
+    if (!workspace || workspace_bytes < rgbd_dv_workspace_bytes(p)) {
+        set_error("rgbd_dv_compute_proj_idcs: workspace too small");
+        return RGBD_E_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = p->W * p->H * p->D;
+    const int nblocks = (n + kThreads - 1) / kThreads;
+    int *counts = (int *)workspace, *offsets = counts + nblocks, *total = offsets + nblocks;
+    k_dv_count<<<nblocks, kThreads, 0, st>>>(*p, cam2world, counts);
+    k_dv_scan<<<1, 1024, 0, st>>>(counts, nblocks, offsets, total);
+    k_dv_compact<<<nblocks, kThreads, 0, st>>>(*p, cam2world, offsets, lin_ind, voxel_coords, n);
+    int rc = check_launch("rgbd_dv_compute_proj_idcs");
+    if (rc) return rc;
+    cudaError_t e = cudaMemcpyAsync(M_host, total, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("rgbd_dv_compute_proj_idcs: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+RGBD_API int rgbd_dv_trilinear_fwd(const float *grid, const int32_t *lin_ind, const float *voxel_coords, int ld, int M,
+                          int F, const rgbd_dv_params *p, float *frustum, void *stream)
+{
+    if (!dv_ok(p) || !grid || !frustum || F <= 0 || M < 0 || (M > 0 && (!lin_ind || !voxel_coords))) {
+        set_error("rgbd_dv_trilinear_fwd: null pointer or bad params");
+        return RGBD_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = p->W * p->H * p->D;
+    cudaError_t e = cudaMemsetAsync(frustum, 0, sizeof(float) * (size_t)F * n, st);   // xp.zeros (:415)
+    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+    if (M > 0)
+        k_dv_trilinear_fwd<<<(M + kThreads - 1) / kThreads, kThreads, 0, st>>>(grid, lin_ind, voxel_coords, ld, M, F,
+                                                                               p->G, n, frustum);
+    return check_launch("rgbd_dv_trilinear_fwd");
+}
+
+RGBD_API int rgbd_dv_trilinear_bwd(const float *g_frustum, const int32_t *lin_ind, const float *voxel_coords, int ld, int M,
+                          int F, const rgbd_dv_params *p, float *g_grid, void *stream)
+{
+    if (!dv_ok(p) || !g_frustum || !g_grid || F <= 0 || M < 0 || (M > 0 && (!lin_ind || !voxel_coords))) {
+        set_error("rgbd_dv_trilinear_bwd: null pointer or bad params");
+        return RGBD_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = p->W * p->H * p->D;
+    const size_t G3 = (size_t)p->G * p->G * p->G;
+    cudaError_t e = cudaMemsetAsync(g_grid, 0, sizeof(float) * (size_t)F * G3, st);
+    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+    if (M > 0)
+        k_dv_trilinear_bwd<<<(M + kThreads - 1) / kThreads, kThreads, 0, st>>>(g_frustum, lin_ind, voxel_coords, ld, M,
+                                                                               F, p->G, n, g_grid);
+    return check_launch("rgbd_dv_trilinear_bwd");
+}
+
+RGBD_API int rgbd_dv_project_fwd(const rgbd_dv_params *p, const float *grid, const float *cam2world, int B, int F,
+                        float *frustum, void *stream)
+{
+    if (!dv_ok(p) || !grid || !cam2world || !frustum || B <= 0 || F <= 0) {
+        set_error("rgbd_dv_project_fwd: null pointer or bad params");
+        return RGBD_E_ARG;
+    }
+    const int n = p->W * p->H * p->D;
+    dim3 grid_dim((n + kThreads - 1) / kThreads, B);
+    k_dv_project_fwd<<<grid_dim, kThreads, 0, (cudaStream_t)stream>>>(*p, grid, cam2world, F, frustum);
+    return check_launch("rgbd_dv_project_fwd");
+}
+
+RGBD_API int rgbd_dv_project_bwd(const rgbd_dv_params *p, const float *g_frustum, const float *cam2world, int B, int F,
+                        float *g_grid, void *stream)
+{
+    if (!dv_ok(p) || !g_frustum || !cam2world || !g_grid || B <= 0 || F <= 0) {
+        set_error("rgbd_dv_project_bwd: null pointer or bad params");
+        return RGBD_E_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = p->W * p->H * p->D;
+    const size_t G3 = (size_t)p->G * p->G * p->G;
+    cudaError_t e = cudaMemsetAsync(g_grid, 0, sizeof(float) * (size_t)B * F * G3, st);
+    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+    dim3 grid_dim((n + kThreads - 1) / kThreads, B);
+    k_dv_project_bwd<<<grid_dim, kThreads, 0, st>>>(*p, g_frustum, cam2world, F, g_grid);
+    return check_launch("rgbd_dv_project_bwd");
+}
+
+}  // extern "C"

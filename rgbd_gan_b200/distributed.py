@@ -1,0 +1,40 @@
+"""Multi-GPU host logic: the batch of PAIRS is sharded over one process per GPU.
+
+Pairs are independent; the only coupling in the reference is the global mean of the loss
+(common/loss_functions.py:141-144 divides by all N = B*HW elements).  Each rank therefore
+runs the kernels on its shard with the GLOBAL pair count baked into the denominators
+(`rgbd_loss_opts.n_pairs_global`), gradients need no communication at all, and the loss is
+finished by one all-reduce(sum) of four floats.  The reference's analogue is ChainerMN's
+`pure_nccl` communicator (train_rgbd.py:103-113), which it uses for weight gradients only.
+"""
+import torch
+import torch.distributed as dist
+
+from .loss_functions import combine_loss_parts
+
+
+def shard_range(n_pairs, rank, world_size):
+    """contiguous, balanced split of `n_pairs` pairs: returns (start, stop) for `rank`.
+    Twins stay together because pair b is (img[b], img_rot[b])."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad rank/world_size")
+    base, rem = divmod(n_pairs, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def allreduce_loss(parts, lambda_geometric, group=None):
+    """parts: tensor whose first four entries are this shard's means {rgb, rgb_rot, depth,
+    depth_rot} computed with global denominators.  Returns (global loss, global parts)."""
+    p = parts[:4].clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(p, op=dist.ReduceOp.SUM, group=group)
+    return combine_loss_parts(p, lambda_geometric), p
+
+
+def max_over_ranks(value, device, group=None):
+    """max of a python float over the group (bench timing rule: report the slowest rank)"""
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

@@ -1,0 +1,382 @@
+"""Host-side mirror of the reference's common/loss_functions.py call surface.
+
+Same names, argument meaning and return values as the reference
+(`LossFuncRotate`, `warp`, `inv_warp`, `bilinear`; reference lines cited per function),
+but every array operation of the reference's Chainer graph is replaced by calls into
+librgbdgan_b200.so (hand-written sm_100a kernels) through ctypes.  Device memory, streams
+and autograd hooks come from torch in this image (the reference's Chainer/CuPy are not
+installable here); `chainer_nodes.py` holds the same glue as Chainer FunctionNodes for a
+deployment that has Chainer + CuPy.  There is no CPU fallback: inputs must be CUDA tensors.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import DvParams, LossOpts  # noqa: F401
+
+
+def _as_numpy(a):
+    """theta / K style inputs: ndarray, torch tensor (any device), or an object with `.array`."""
+    if hasattr(a, "array") and not isinstance(a, np.ndarray):
+        a = a.array
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    return np.asarray(a)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f32(t, what):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA tensor (rgbd_gan_b200 has no CPU path)" % what)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (what, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def pose_algebra(K, inv_K, theta, theta_rot):
+    """common/loss_functions.py:85-91 and the constant factors of warp (:174) / inv_warp (:181),
+    evaluated with the same NumPy matmul sequence on the host.
+    Returns float32 arrays M (B,3,3), c (B,3,1), Mi (B,3,3), ci (B,3,1) with the convention of
+    include/rgbdgan_b200.h: new_zp = M (z p) - c ; new_zp_rot = Mi (z_rot p) - ci  (ci = -(K t))."""
+    theta, theta_rot = _as_numpy(theta), _as_numpy(theta_rot)
+    R1, R2 = theta[:, :3, :3], theta_rot[:, :3, :3]
+    t1, t2 = theta[:, :3, -1:], theta_rot[:, :3, -1:]
+    R = np.matmul(R2.transpose(0, 2, 1), R1).astype("float32")
+    inv_R = R.transpose(0, 2, 1)
+    t = np.matmul(R1.transpose(0, 2, 1), t2 - t1).astype("float32")
+    M = np.matmul(np.matmul(K, R), inv_K)
+    c = np.matmul(np.matmul(K, R), t)
+    Mi = np.matmul(np.matmul(K, inv_R), inv_K)
+    ci = -np.matmul(K, t)
+    return (np.ascontiguousarray(M, dtype=np.float32), np.ascontiguousarray(c, dtype=np.float32),
+            np.ascontiguousarray(Mi, dtype=np.float32), np.ascontiguousarray(ci, dtype=np.float32))
+
+
+class _PoseUploader:
+    """Packs M|c|Mi|ci (24 floats per pair) into pinned memory and copies it asynchronously."""
+
+    def __init__(self):
+        self._slots = {}
+
+    def upload(self, M, c, Mi, ci, device):
+        B = M.shape[0]
+        key = (B, str(device))
+        if key not in self._slots:
+            self._slots[key] = dict(bufs=[torch.empty(24 * B, dtype=torch.float32).pin_memory() for _ in range(2)],
+                                    events=[None, None], k=0)
+        s = self._slots[key]
+        k = s["k"]
+        s["k"] = 1 - k
+        if s["events"][k] is not None:
+            s["events"][k].synchronize()          # the copy that last used this slot has finished
+        host = s["bufs"][k]
+        hv = host.numpy()
+        hv[0:9 * B] = M.reshape(-1)
+        hv[9 * B:12 * B] = c.reshape(-1)
+        hv[12 * B:21 * B] = Mi.reshape(-1)
+        hv[21 * B:24 * B] = ci.reshape(-1)
+        dev = host.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        s["events"][k] = ev
+        return dev
+
+
+def _pose_ptrs(dev, B):
+    base = dev.data_ptr()
+    return [ctypes.c_void_p(base + 4 * off) for off in (0, 9 * B, 12 * B, 21 * B)]
+
+
+class _ConsistencyFn(torch.autograd.Function):
+    """LossFuncRotate.__call__ body (common/loss_functions.py:93-146) as one autograd node."""
+
+    @staticmethod
+    def forward(ctx, img, img_rot, owner, poses, opts, want_zp):
+        B, C, H, W = img.shape
+        dev = img.device
+        ws = owner._workspace(B, C, H, W, dev)
+        parts = torch.empty(8, dtype=torch.float32, device=dev)
+        new_zp = torch.empty((2 * B, H * W, 3), dtype=torch.float32, device=dev) if want_zp else None
+        pp = _pose_ptrs(poses, B)
+        need_grad = img.requires_grad or img_rot.requires_grad
+        ctx.owner, ctx.opts, ctx.poses, ctx.shape = owner, opts, poses, (B, C, H, W)
+        ctx.fused = owner.grad_scale is not None and need_grad
+        ctx.set_materialize_grads(False)
+        if ctx.fused:
+            g_img, g_img_rot = torch.empty_like(img), torch.empty_like(img_rot)
+            _lib.call("rgbd_consistency_fwd_bwd", _ptr(img), _ptr(img_rot), *pp, B, C, H, W, ctypes.byref(opts),
+                      ctypes.c_float(owner.grad_scale), _ptr(parts), _ptr(new_zp), _ptr(g_img), _ptr(g_img_rot),
+                      _ptr(ws), ws.numel(), _stream())
+            ctx.stash = (g_img, g_img_rot)
+        else:
+            _lib.call("rgbd_consistency_fwd", _ptr(img), _ptr(img_rot), *pp, B, C, H, W, ctypes.byref(opts),
+                      _ptr(parts), _ptr(new_zp), None, _ptr(ws), ws.numel(), _stream())
+        ctx.save_for_backward(img, img_rot)
+        owner.last_loss_parts = parts
+        if owner.process_group is not None:
+            loss = owner._allreduce_combine(parts)
+        else:
+            loss = parts[4].clone()
+        if new_zp is None:
+            return loss, None
+        return loss, new_zp
+
+    @staticmethod
+    def backward(ctx, g_loss, g_new_zp=None):
+        img, img_rot = ctx.saved_tensors
+        B, C, H, W = ctx.shape
+        owner = ctx.owner
+        if g_loss is None:
+            g_loss = torch.zeros((), dtype=torch.float32, device=img.device)
+        g_loss = g_loss.to(torch.float32).contiguous()
+        if ctx.fused and g_new_zp is None:
+            g_img, g_img_rot = ctx.stash
+            _lib.call("rgbd_consistency_rescale", _ptr(g_img), _ptr(g_img_rot), g_img.numel(), _ptr(g_loss),
+                      ctypes.c_float(owner.grad_scale), _stream())
+            return g_img, g_img_rot, None, None, None, None
+        ws = owner._workspace(B, C, H, W, img.device)
+        g_img, g_img_rot = torch.empty_like(img), torch.empty_like(img_rot)
+        gz = None if g_new_zp is None else g_new_zp.to(torch.float32).contiguous()
+        _lib.call("rgbd_consistency_bwd", _ptr(img), _ptr(img_rot), *_pose_ptrs(ctx.poses, B), B, C, H, W,
+                  ctypes.byref(ctx.opts), ctypes.c_float(1.0), _ptr(g_loss), _ptr(gz), _ptr(g_img), _ptr(g_img_rot),
+                  _ptr(ws), ws.numel(), _stream())
+        return g_img, g_img_rot, None, None, None, None
+
+
+class LossFuncRotate:
+    """Mirror of the reference class (common/loss_functions.py:31-168).
+
+    Extra keyword-only arguments (not in the reference):
+      grad_scale      -- if set, forward also produces both image gradients for this upstream
+                         gradient in the same pass (rgbd_consistency_fwd_bwd); backward then
+                         only checks the gradient that arrives (device side) and rescales if it
+                         differs.  In the reference's loop the upstream gradient of this loss is
+                         the constant lambda_rotate (updater.py:363-365).
+      return_new_zp   -- materialise the second return value (:146).  No reference caller uses
+                         it (updater.py:340 drops it); False returns None in its place.
+      process_group   -- torch.distributed group over which the PAIRS are sharded; the four
+                         loss means are all-reduced (4 floats), gradients need no communication.
+    """
+
+    def __init__(self, xp=None, K=None, norm="l1", lambda_geometric=3, *, grad_scale=None, return_new_zp=True,
+                 process_group=None):
+        self.xp = xp
+        self.size = None
+        self.K = K
+        self.norm = norm
+        self.lambda_geometric = lambda_geometric
+        self.inv_K = None
+        self.p = None
+        self.grad_scale = None if grad_scale is None else float(grad_scale)
+        self.return_new_zp = return_new_zp
+        self.process_group = process_group
+        self.last_loss_parts = None
+        self._uploader = _PoseUploader()
+        self._ws = {}
+
+    # -- :39-61
+    def init_params(self, xp=None, size=4):
+        if self.size is None:
+            if self.K is not None:
+                self.K = np.array(_as_numpy(self.K)[:3, :3], "float32")
+                self.K[:2] *= size / self.K[0, 2] / 2
+                self.size = size
+            else:
+                self.size = size
+                self.K = np.array([[size * 2, 0, size / 2],
+                                   [0, size * 2, size / 2],
+                                   [0, 0, 1]], dtype="float32")
+        else:
+            self.size = size
+            self.K[:2] *= size / self.K[0, 2] / 2          # in place: state carries across stages (quirk Q9)
+        self.inv_K = np.linalg.inv(self.K).astype("float32")
+        self.p = np.asarray(list(np.meshgrid(np.arange(size), np.arange(size))) + [np.ones((size, size))],
+                            dtype="float32").reshape(3, -1)
+
+    def _workspace(self, B, C, H, W, device):
+        key = (B, C, H, W, str(device))
+        ws = self._ws.get(key)
+        if ws is None:
+            nbytes = _lib.load().rgbd_consistency_workspace_bytes(B, C, H, W)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._ws = {key: ws}                       # keep one size only
+        return ws
+
+    def _opts(self, occlusion_aware, max_depth, min_depth, B):
+        world = 1
+        if self.process_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.process_group)
+        return LossOpts(_lib.NORM_L1 if self.norm == "l1" else _lib.NORM_L2, int(bool(occlusion_aware)),
+                        float("nan") if max_depth is None else float(max_depth),
+                        float("nan") if min_depth is None else float(min_depth),
+                        float(self.lambda_geometric), int(B) * world)
+
+    def _allreduce_combine(self, parts):
+        """sum the four per-shard means over the group, then combine as :141-144 (fp32)"""
+        import torch.distributed as dist
+        p = parts[:4].clone()
+        dist.all_reduce(p, op=dist.ReduceOp.SUM, group=self.process_group)
+        return combine_loss_parts(p, self.lambda_geometric)
+
+    # -- :63-146
+    def __call__(self, img, theta, img_rot, theta_rot, occlusion_aware=False, debug=False, max_depth=None,
+                 min_depth=None):
+        img = _dev_f32(img, "img")
+        img_rot = _dev_f32(img_rot, "img_rot")
+        if img.shape != img_rot.shape or img.dim() != 4:
+            raise ValueError("img and img_rot must both be (B,C,H,W)")
+        if img.shape[-1] != img.shape[-2]:
+            raise ValueError("the reference's intrinsics assume square images (loss_functions.py:48-61)")
+        if self.size != img.shape[-1]:
+            self.init_params(self.xp, size=img.shape[-1])
+        B, C, H, W = img.shape
+        M, c, Mi, ci = pose_algebra(self.K, self.inv_K, theta, theta_rot)
+        if debug:
+            return self._debug(img, img_rot, M, c, Mi, ci)
+        poses = self._uploader.upload(M, c, Mi, ci, img.device)
+        opts = self._opts(occlusion_aware, max_depth, min_depth, B)
+        return _ConsistencyFn.apply(img, img_rot, self, poses, opts, bool(self.return_new_zp))
+
+    def _debug(self, img, img_rot, M, c, Mi, ci):
+        """:100-102 -- warped images / masks for eyeballing"""
+        B, C, H, W = img.shape
+        dev = img.device
+        z = img[:, -1:].reshape(B, 1, -1)
+        z_rot = img_rot[:, -1:].reshape(B, 1, -1)
+        new_zp = _WarpFn.apply(z, torch.from_numpy(M).to(dev), torch.from_numpy(c).to(dev), H, W)
+        new_zp_rot = _WarpFn.apply(z_rot, torch.from_numpy(Mi).to(dev), torch.from_numpy(ci).to(dev), H, W)
+        warped, not_out = bilinear(img_rot, new_zp)
+        warped_rot, not_out_rot = bilinear(img, new_zp_rot)
+        return warped, not_out, new_zp, warped_rot, not_out_rot, new_zp_rot
+
+    # -- :148-158 (no caller in the reference; plain array-library math)
+    def calc_real_pos(self, img, theta):
+        theta = _as_numpy(theta)
+        if theta.ndim == 1:
+            assert False, "only rotation matrices are supported for theta"
+        dev = img.device
+        R = torch.from_numpy(np.ascontiguousarray(theta[:, :3, :3], dtype=np.float32)).to(dev)
+        t = torch.from_numpy(np.ascontiguousarray(theta[:, :3, -1:], dtype=np.float32)).to(dev)
+        z = img[:, -1:].detach().reshape(img.shape[0], 1, -1)
+        rgb = img[:, :3].detach().reshape(img.shape[0], 3, -1)
+        inv_K, p = torch.from_numpy(self.inv_K).to(dev), torch.from_numpy(self.p).to(dev)
+        real_pos = torch.matmul(torch.matmul(R, inv_K), z * p) + t
+        return torch.cat([rgb, real_pos], dim=1)
+
+    # -- :160-168 (only with `use_occupancy_net_loss`, absent from every shipped config)
+    def occupancy_net_loss(self, occupancy_net, depth, theta, z):
+        theta = _as_numpy(theta)
+        dev = depth.device
+        R = torch.from_numpy(np.ascontiguousarray(theta[:, :3, :3], dtype=np.float32)).to(dev)
+        t = torch.from_numpy(np.ascontiguousarray(theta[:, :3, -1:], dtype=np.float32)).to(dev)
+        depth = depth.reshape(depth.shape[0], 1, -1)
+        eps = torch.randn(depth.shape, device=dev) * 0.05
+        inv_K, p = torch.from_numpy(self.inv_K).to(dev), torch.from_numpy(self.p).to(dev)
+        real_pos = torch.matmul(torch.matmul(R, inv_K), (depth + eps) * p) + t
+        label = (eps > 0).reshape(-1, 1).to(torch.float32)
+        occupancy_field = occupancy_net(z, real_pos + eps)
+        return torch.nn.functional.binary_cross_entropy_with_logits(occupancy_field, label)
+
+
+def combine_loss_parts(parts, lambda_geometric):
+    """loss = (rgb + rgb_rot) + (depth*lambda + depth_rot*lambda), fp32 (:141-144).
+    `parts`: tensor/array of the four means (summed over shards)."""
+    lam = float(lambda_geometric)
+    return (parts[0] + parts[1]) + (parts[2] * lam + parts[3] * lam)
+
+
+# ------------------------------------------------------------------------------ free functions
+class _WarpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, M, cv, H, W):
+        B = z.shape[0]
+        zc = _dev_f32(z, "z").reshape(B, H * W)
+        M = M.contiguous()
+        cv = cv.contiguous()
+        out = torch.empty((B, H * W, 3), dtype=torch.float32, device=z.device)
+        _lib.call("rgbd_warp_fwd", _ptr(zc), _ptr(M), _ptr(cv), B, H, W, _ptr(out), _stream())
+        ctx.M, ctx.dims, ctx.zshape = M, (B, H, W), z.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, W = ctx.dims
+        g = g.to(torch.float32).contiguous()
+        gz = torch.empty((B, H * W), dtype=torch.float32, device=g.device)
+        _lib.call("rgbd_warp_bwd", _ptr(g), _ptr(ctx.M), B, H, W, _ptr(gz), _stream())
+        return gz.reshape(ctx.zshape), None, None, None, None
+
+
+def _grid_dims(p, hw):
+    p = _as_numpy(p)
+    if p.shape != (3, hw):
+        raise ValueError("p must be (3, H*W)")
+    W, H = int(p[0].max()) + 1, int(p[1].max()) + 1
+    if W * H != hw:
+        raise ValueError("p is not a full pixel grid")
+    return H, W
+
+
+def warp(K, inv_K, R, t, z, p):
+    """common/loss_functions.py:171-175: (K R K^-1)(z p) - (K R) t, returned as (B,HW,3). Differentiable in z."""
+    K, inv_K, R, t = (_as_numpy(a).astype("float32") for a in (K, inv_K, R, t))
+    H, W = _grid_dims(p, z.shape[-1])
+    M = np.ascontiguousarray(np.matmul(np.matmul(K, R), inv_K), dtype=np.float32)
+    cv = np.ascontiguousarray(np.matmul(np.matmul(K, R), t), dtype=np.float32)
+    return _WarpFn.apply(z, torch.from_numpy(M).to(z.device), torch.from_numpy(cv).to(z.device), H, W)
+
+
+def inv_warp(K, inv_K, inv_R, t, z, p):
+    """common/loss_functions.py:178-182: (K R^T K^-1)(z p) + K t, returned as (B,HW,3). Differentiable in z."""
+    K, inv_K, inv_R, t = (_as_numpy(a).astype("float32") for a in (K, inv_K, inv_R, t))
+    H, W = _grid_dims(p, z.shape[-1])
+    M = np.ascontiguousarray(np.matmul(np.matmul(K, inv_R), inv_K), dtype=np.float32)
+    cv = np.ascontiguousarray(-np.matmul(K, t), dtype=np.float32)
+    return _WarpFn.apply(z, torch.from_numpy(M).to(z.device), torch.from_numpy(cv).to(z.device), H, W)
+
+
+class _BilinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, zp):
+        B, C, H, W = img.shape
+        warped = torch.empty((B * H * W, C), dtype=torch.float32, device=img.device)
+        mask = torch.empty(B * H * W, dtype=torch.uint8, device=img.device)
+        _lib.call("rgbd_bilinear_fwd", _ptr(img), _ptr(zp), B, C, H, W, _ptr(warped), _ptr(mask), _stream())
+        ctx.save_for_backward(img, zp)
+        mask = mask.bool()
+        ctx.mark_non_differentiable(mask)
+        return warped, mask
+
+    @staticmethod
+    def backward(ctx, g_warped, _g_mask=None):
+        img, zp = ctx.saved_tensors
+        B, C, H, W = img.shape
+        g_warped = g_warped.to(torch.float32).contiguous()
+        g_img = torch.empty_like(img)
+        g_zp = torch.empty_like(zp)
+        _lib.call("rgbd_bilinear_bwd", _ptr(img), _ptr(zp), _ptr(g_warped), B, C, H, W, _ptr(g_img), _ptr(g_zp),
+                  _stream())
+        return g_img, g_zp
+
+
+def bilinear(img, zp):
+    """common/loss_functions.py:185-228 -> (warped (B*HW, C), not_getting_out (B*HW,) bool)."""
+    img = _dev_f32(img, "img")
+    zp = _dev_f32(zp, "zp")
+    b, hw, _ = zp.shape
+    if img.shape[0] != b or img.shape[2] * img.shape[3] != hw:
+        raise ValueError("zp must be (B, H*W, 3) matching img (B,C,H,W)")
+    return _BilinearFn.apply(img, zp)
+
+
+__all__ = ["LossFuncRotate", "warp", "inv_warp", "bilinear", "pose_algebra", "combine_loss_parts"]

@@ -1,0 +1,141 @@
+"""GPU: the Python mirror of the reference call surface (rgbd_gan_b200.loss_functions / projection),
+driven the way updater.py / deepvoxels_generator.py drive the reference, checked against the golden
+vectors of the unmodified reference."""
+import numpy as np
+import pytest
+
+from conftest import DV_CASES, LOSS_CASES, assert_grad_close, case_options, load_golden
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+DEV = "cuda:0"
+
+
+def _run(name, **ctor):
+    from rgbd_gan_b200.loss_functions import LossFuncRotate
+    g = load_golden(name)
+    o = case_options(g)
+    B = o["B"]
+    x = torch.from_numpy(g["x"]).to(DEV)
+    img = x[:B].clone().requires_grad_(True)
+    img_rot = x[B:].clone().requires_grad_(True)
+    f = LossFuncRotate(None, K=None if o["K"] is None else o["K"].copy(), norm=o["norm"], lambda_geometric=o["lam"],
+                       **ctor)
+    kw = dict(occlusion_aware=o["occ"])
+    if o["max_depth"] is not None:
+        kw["max_depth"] = o["max_depth"]
+    if o["min_depth"] is not None:
+        kw["min_depth"] = o["min_depth"]
+    loss, zp = f(img, g["cam"][:B], img_rot, g["cam"][B:], **kw)
+    (loss * o["gy"]).backward()            # loss_gen += loss_rotate * lambda_rotate; loss_gen.backward()
+    return g, o, f, loss, zp, img.grad, img_rot.grad
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_loss_func_rotate_like_updater(name):
+    g, o, f, loss, zp, gi, gr = _run(name)
+    assert loss.dim() == 0
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    np.testing.assert_array_equal(zp.detach().cpu().numpy(), g["new_zp_cat"])
+    assert_grad_close(gi.cpu().numpy(), g["g_img"])
+    assert_grad_close(gr.cpu().numpy(), g["g_img_rot"])
+    np.testing.assert_array_equal(f.K, g["K"])
+    np.testing.assert_array_equal(f.inv_K, g["inv_K"])
+
+
+@pytest.mark.parametrize("name", ["loss_cfg0_l1_occ", "loss_s32_l2_feat", "loss_dv_mindepth"])
+@pytest.mark.parametrize("scale", [2.0, 0.5])
+def test_fused_grad_scale_path(name, scale):
+    """grad_scale = the expected upstream gradient: exact when it matches (2.0 = golden gy), rescaled when not"""
+    g, o, f, loss, zp, gi, gr = _run(name, grad_scale=scale, return_new_zp=False)
+    assert zp is None
+    assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert_grad_close(gi.cpu().numpy(), g["g_img"])
+    assert_grad_close(gr.cpu().numpy(), g["g_img_rot"])
+
+
+def test_debug_tuple_and_free_functions():
+    from rgbd_gan_b200.loss_functions import LossFuncRotate, bilinear, inv_warp, warp
+    g = load_golden("loss_cfg0_l1_occ")
+    o = case_options(g)
+    B, S = o["B"], o["S"]
+    x = torch.from_numpy(g["x"]).to(DEV)
+    f = LossFuncRotate(None, lambda_geometric=o["lam"])
+    out = f(x[:B], g["cam"][:B], x[B:], g["cam"][B:], debug=True)
+    warped, not_out, new_zp, warped_rot, not_out_rot, new_zp_rot = out
+    np.testing.assert_array_equal(warped.cpu().numpy(), g["warped"])
+    np.testing.assert_array_equal(warped_rot.cpu().numpy(), g["warped_rot"])
+    np.testing.assert_array_equal(not_out.cpu().numpy(), g["not_out"])
+    np.testing.assert_array_equal(not_out_rot.cpu().numpy(), g["not_out_rot"])
+    np.testing.assert_array_equal(torch.cat([new_zp, new_zp_rot]).cpu().numpy(), g["new_zp_cat"])
+    # free functions with the reference's argument lists (loss_functions.py:89-94)
+    cam = g["cam"]
+    R1, R2 = cam[:B, :3, :3], cam[B:, :3, :3]
+    t1, t2 = cam[:B, :3, -1:], cam[B:, :3, -1:]
+    R = np.matmul(R2.transpose(0, 2, 1), R1).astype("float32")
+    t = np.matmul(R1.transpose(0, 2, 1), t2 - t1).astype("float32")
+    z = x[:B, -1:].reshape(B, 1, -1).clone().requires_grad_(True)
+    z_rot = x[B:, -1:].reshape(B, 1, -1)
+    zp = warp(f.K, f.inv_K, R, t, z, f.p)
+    zp_rot = inv_warp(f.K, f.inv_K, R.transpose(0, 2, 1), t, z_rot, f.p)
+    np.testing.assert_array_equal(torch.cat([zp, zp_rot]).detach().cpu().numpy(), g["new_zp_cat"])
+    img_rot = x[B:].clone().requires_grad_(True)
+    w, m = bilinear(img_rot, zp)
+    np.testing.assert_array_equal(w.detach().cpu().numpy(), g["warped"])
+    # composing the free functions and autograd gives the fused gradients (no occlusion variant)
+    from oracle import numpy_port as npp
+    gw = torch.from_numpy(np.random.default_rng(0).normal(size=tuple(w.shape)).astype(np.float32)).to(DEV)
+    (w * gw).sum().backward()
+    _, _, tape = npp.LossFuncRotateNP._bilinear_fwd(g["x"][B:], zp.detach().cpu().numpy())
+    gi_ref, gzp_ref = npp.LossFuncRotateNP._bilinear_bwd(tape, gw.cpu().numpy())
+    assert_grad_close(img_rot.grad.cpu().numpy(), gi_ref)
+    port = npp.LossFuncRotateNP()
+    port.init_params(S)
+    M = port.pose_algebra(cam[:B], cam[B:])[0]
+    gzp_ref[:, :, 1] = 0
+    gz_ref = (np.matmul(M.transpose(0, 2, 1), gzp_ref.transpose(0, 2, 1)) * port.p).sum(axis=1, keepdims=True)
+    assert_grad_close(z.grad.cpu().numpy(), gz_ref, tol=2e-5)
+
+
+def test_growing_instance_state():
+    from rgbd_gan_b200.loss_functions import LossFuncRotate
+    g = load_golden("loss_growing")
+    B = int(g["B"])
+    f = LossFuncRotate(None)
+    for S in (32, 64):
+        x = torch.from_numpy(g["x%d" % S]).to(DEV)
+        img, img_rot = x[:B].clone().requires_grad_(True), x[B:].clone().requires_grad_(True)
+        loss, zp = f(img, g["cam"][:B], img_rot, g["cam"][B:], occlusion_aware=True)
+        loss.backward()
+        assert abs(loss.item() - float(g["loss_%d" % S])) <= 1e-5 * float(g["loss_%d" % S])
+        np.testing.assert_array_equal(f.K, g["K_%d" % S])
+        assert_grad_close(img.grad.cpu().numpy(), g["g_img_%d" % S])
+
+
+@pytest.mark.parametrize("name", DV_CASES)
+def test_projection_helper_like_generator(name):
+    from rgbd_gan_b200.projection import ProjectionHelper, interpolate_trilinear
+    g = load_golden(name)
+    G, img, F, D = int(g["G"]), int(g["img"]), int(g["F"]), int(g["D"])
+    h = ProjectionHelper(g["intrinsic"], g["intrinsic"], [img, img], [img, img], 0., 1., [G] * 3,
+                         float(g["voxel_size"]), g["near_plane"], D, verbose=False)
+    ns = g["cam"].shape[0]
+    for i in range(ns):
+        lin, vc = h.compute_proj_idcs(g["cam"][i])
+        np.testing.assert_array_equal(lin.cpu().numpy(), g["lin_ind_%d" % i])
+        np.testing.assert_array_equal(vc.cpu().numpy(), g["voxel_coords_%d" % i])
+        grid = torch.from_numpy(g["grid"][i:i + 1]).to(DEV).requires_grad_(True)
+        out = interpolate_trilinear(grid, lin, vc, [img, img], D)
+        assert tuple(out.shape) == (1, F, D, img, img)
+        np.testing.assert_array_equal(out.detach().cpu().numpy(), g["frustum_%d" % i])
+        out.backward(torch.from_numpy(g["g_out"][i:i + 1]).to(DEV))
+        assert_grad_close(grid.grad.cpu().numpy(), g["g_grid_%d" % i])
+    grid = torch.from_numpy(g["grid"]).to(DEV).requires_grad_(True)
+    fr = h.project(grid, g["cam"])
+    fr.backward(torch.from_numpy(g["g_out"]).to(DEV))
+    for i in range(ns):
+        np.testing.assert_array_equal(fr[i].detach().cpu().numpy(), g["frustum_%d" % i][0])
+        assert_grad_close(grid.grad[i].cpu().numpy(), g["g_grid_%d" % i][0])
+    cam = g["cam"][0].copy()
+    cam[:3, 3] += 100.0
+    assert h.compute_proj_idcs(cam) is None

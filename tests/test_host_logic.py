@@ -1,0 +1,135 @@
+"""CPU: host-side logic of the product package (no compute calls: there is no GPU here) and the
+C-ABI library's exported symbols."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import LOSS_CASES, ROOT, case_options, load_golden
+from oracle import numpy_port as npp
+
+
+def test_library_builds_and_exports_header_symbols():
+    from rgbd_gan_b200 import _lib, build
+    path = build.build()
+    assert os.path.exists(path)
+    hdr = open(os.path.join(ROOT, "include", "rgbdgan_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rgbd_[a-z_0-9]+)\s*\(", hdr))
+    assert len(declared) >= 17
+    lib = ctypes.CDLL(path)                       # loads without a GPU (the CUDA runtime is linked statically)
+    for name in declared:
+        assert hasattr(lib, name), "missing export: " + name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib.rgbd_version.restype = ctypes.c_int
+    assert lib.rgbd_version() == 100
+    # pure host queries work without a device
+    lib.rgbd_consistency_workspace_bytes.restype = ctypes.c_size_t
+    assert lib.rgbd_consistency_workspace_bytes(4, 4, 128, 128) > 2 * 2 * 4 * 4 * 128 * 128 * 4
+    assert lib.rgbd_consistency_workspace_bytes(0, 4, 128, 128) == 0
+
+
+def test_argument_errors_are_reported_not_raised():
+    from rgbd_gan_b200 import _lib
+    lib = _lib.load()
+    opts = _lib.LossOpts(1, 1, float("nan"), float("nan"), 3.0, 0)
+    rc = lib.rgbd_consistency_fwd(None, None, None, None, None, None, 1, 4, 8, 8, ctypes.byref(opts), None, None, None,
+                                  None, 0, None)
+    assert rc == -1 and b"null" in lib.rgbd_last_error()
+    with pytest.raises(_lib.RgbdB200Error):
+        _lib.check(rc, "rgbd_consistency_fwd")
+
+
+def test_no_cpu_fallback():
+    torch = pytest.importorskip("torch")
+    from rgbd_gan_b200.loss_functions import LossFuncRotate, bilinear
+    x = torch.zeros(1, 4, 8, 8)
+    cam = np.tile(np.eye(4, dtype=np.float32), (1, 1, 1))
+    with pytest.raises(TypeError):
+        LossFuncRotate(None)(x, cam, x, cam)
+    with pytest.raises(TypeError):
+        bilinear(x, torch.zeros(1, 64, 3))
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_pose_algebra_matches_reference_intermediates(name):
+    """product host code == oracle port; K/inv_K/p == what the reference computed"""
+    from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
+    g = load_golden(name)
+    o = case_options(g)
+    B, S = o["B"], o["S"]
+    obj = LossFuncRotate(None, K=None if o["K"] is None else o["K"].copy(), norm=o["norm"], lambda_geometric=o["lam"])
+    obj.init_params(None, size=S)
+    np.testing.assert_array_equal(obj.K, g["K"])
+    np.testing.assert_array_equal(obj.inv_K, g["inv_K"])
+    np.testing.assert_array_equal(obj.p, g["p"])
+    port = npp.LossFuncRotateNP(K=None if o["K"] is None else o["K"].copy())
+    port.init_params(S)
+    M, c, Mi, ci = pose_algebra(obj.K, obj.inv_K, g["cam"][:B], g["cam"][B:])
+    M2, c2, Mi2, ci2 = port.pose_algebra(g["cam"][:B], g["cam"][B:])
+    np.testing.assert_array_equal(M, M2)
+    np.testing.assert_array_equal(c, c2)
+    np.testing.assert_array_equal(Mi, Mi2)
+    np.testing.assert_array_equal(ci, -ci2)
+
+
+def test_growing_state_product_host():
+    from rgbd_gan_b200.loss_functions import LossFuncRotate
+    g = load_golden("loss_growing")
+    obj = LossFuncRotate(None)
+    for S in (32, 64):
+        obj.init_params(None, size=S)
+        np.testing.assert_array_equal(obj.K, g["K_%d" % S])
+        np.testing.assert_array_equal(obj.inv_K, g["inv_K_%d" % S])
+        assert obj.size == S
+
+
+@pytest.mark.parametrize("name,seed,ranges,uniform", [
+    ("loss_cfg0_l1_occ", 0, (0.3054, 1.0472, 0, 0, 0, 0), None),
+    ("loss_car_l1_occ", 1, (0.3054, 3.1415, 0, 0, 0, 0), None),
+    ("loss_dv_maxdepth", 5, (0.3054, 3.1415, 0, 0, 0, 0), True),
+    ("loss_edge_wild", 7, (0.3054, 3.1415, 0, 0.3, 0.2, 0.4), None),
+])
+def test_pose_generators_replay_reference(name, seed, ranges, uniform):
+    """CameraParamPrior.sample + get_camera_matries, replayed with the reference's seed, reproduce
+    the thetas / cam2world matrices the reference's own helpers produced (make_golden.py)."""
+    from rgbd_gan_b200 import poses
+    g = load_golden(name)
+    np.random.seed(seed)
+    thetas = poses.CameraParamPrior.from_ranges(ranges, uniform).sample(g["thetas"].shape[0])
+    np.testing.assert_array_equal(thetas, g["thetas"])
+    np.testing.assert_array_equal(poses.get_camera_matries(thetas), g["cam"])
+    np.random.seed(seed)
+    np.testing.assert_array_equal(npp.sample_camera_prior(g["thetas"].shape[0], ranges, bool(uniform)), g["thetas"])
+    np.testing.assert_array_equal(npp.get_camera_matries(g["thetas"]), g["cam"])
+
+
+def test_shard_range():
+    from rgbd_gan_b200.distributed import shard_range
+    for n in (1, 7, 16, 64, 256):
+        for w in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 4, 4)
+
+
+def test_dv_params_follow_generator_constants():
+    """deepvoxels_generator.py:229-253 constants -> rgbd_dv_params"""
+    from rgbd_gan_b200.projection import ProjectionHelper
+    G = 32
+    intr = np.array([[128., 0, 32., 0], [0, 128., 32., 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+    vs = (1. / G) * 1.1 * 0.5
+    h = ProjectionHelper(intr, intr, [64, 64], [64, 64], 0., G * vs + np.sqrt(3) / 4, [G] * 3, vs, np.sqrt(3) / 4,
+                         int(np.ceil(np.sqrt(3) * G)), verbose=False)
+    P = h.params()
+    assert (P.W, P.H, P.D, P.G) == (64, 64, 56, 32)
+    assert P.fx == 128.0 and P.cx == 32.0
+    assert P.voxel_size == np.float32(vs) and P.near_plane == np.float32(np.sqrt(3) / 4)
+    with pytest.raises(ValueError):
+        ProjectionHelper(intr, intr, [64, 64], [64, 64], 0., 1., [32, 32, 16], vs, 0.4, 56, verbose=False)
