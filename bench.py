@@ -1,0 +1,463 @@
+#!/usr/bin/env python3
+"""bench.py -- throughput of the 3D-consistency hot path (fwd + bwd) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--pairs B] [--size S] [--depth rough|smooth] [--no-graph] [--no-sweep]
+
+One "step" = one pass of the hot path over one batch of B synthetic RGB-D pairs: the consistency
+loss (both warp directions, occlusion mask) AND the gradients w.r.t. both 4-channel images.
+Default workload = BASELINE.json configs[1] (ffhq_stylegan_occlusion.yml: batch 32 at 128x128,
+L1, occlusion on, lambda_geometric 3, poses from the yml's CameraParamPrior ranges).
+
+Prints ONE JSON line (rank 0): metric/value (device-resident inputs, CUDA-event timed, max over
+ranks), e2e (public API, host buffers, H2D + D2H inside the timed region), roofline of the dominant
+kernel, cpu_baseline (NumPy port of the Chainer CPU path on this box's host cores) and clocks.
+`--impl reference` times that CPU port alone on the same workload definition.
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "warped RGB-D pairs/sec fwd+bwd at 128^2"
+UNIT = "pairs/s"
+L2_BYTES = 126 * 2 ** 20
+LAMBDA_ROTATE = 2.0          # upstream gradient of the loss: updater.py:363 (lambda_rotate default 2)
+LAMBDA_GEO = 3.0             # updater.py:238
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------- CPU reference arm
+def _cpu_worker(args):
+    """one fwd+bwd of the NumPy port (the Chainer CPU path's array work) on `pairs` pairs"""
+    pairs, S, depth, seed, reps = args
+    from oracle import numpy_port as npp
+    from rgbd_gan_b200 import poses
+    x, cam = poses.synthetic_batch(pairs, S, depth=depth, seed=seed)
+    f = npp.LossFuncRotateNP(lambda_geometric=LAMBDA_GEO)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        f.forward(x[:pairs], cam[:pairs], x[pairs:], cam[pairs:], occlusion_aware=True)
+        f.backward(LAMBDA_ROTATE)
+    return time.perf_counter() - t0
+
+
+def cpu_port_throughput(S, depth, steps, warmup, sample_pairs=4, procs=None):
+    """pairs/s of the NumPy port with one process per host core (NumPy's elementwise kernels are
+    single-threaded, so data-parallel processes are how this path can use every core)."""
+    import multiprocessing as mp
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs) as pool:
+        if warmup:
+            pool.map(_cpu_worker, [(sample_pairs, S, depth, 100 + i, warmup) for i in range(procs)])
+        t0 = time.perf_counter()
+        pool.map(_cpu_worker, [(sample_pairs, S, depth, i, steps) for i in range(procs)])
+        dt = time.perf_counter() - t0
+    return procs * sample_pairs * steps / dt, dt / steps, procs
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    S = a.size
+    steps, warmup = max(1, min(a.steps, 8)), max(0, min(a.warmup, 2))
+    sample = 4
+    value, s_per_step, procs = cpu_port_throughput(S, a.depth, steps, warmup, sample_pairs=sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, a.pairs),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": "oracle/numpy_port.py (op-by-op NumPy port of the Chainer CPU path; Chainer is not "
+                                   "installable here), %d processes x %d pairs per step, %d steps, numpy %s"
+                                   % (procs, sample, steps, np.__version__)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(a, pairs):
+    return {"workload": "configs[1] ffhq_stylegan_occlusion.yml consistency loss fwd+bwd, occlusion mask on, L1, "
+                        "lambda_geometric 3", "pairs_per_gpu": pairs, "size": a.size, "channels": 4,
+            "depth": a.depth, "pose_ranges": "x 0.3054 / y 1.0472 rad (yml)", "upstream_grad": LAMBDA_ROTATE}
+
+
+# ------------------------------------------------------------------------------------ clock sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:           # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"GpuIdle": 0x1, "ApplicationsClocksSetting": 0x2, "sw_power_cap": 0x4, "hw_slowdown": 0x8,
+                 "SyncBoost": 0x10, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80, "DisplayClockSetting": 0x100}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:        # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit and k != "GpuIdle":
+                        self.reasons.add(k)
+            except Exception:            # noqa: BLE001
+                pass
+            self._stop_evt.wait(0.002)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from rgbd_gan_b200 import _lib, poses
+    from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    B, S, C = a.pairs, a.size, 4
+    HW = S * S
+    hbm_peak, peak_src = peaks()
+
+    # ---- synthetic input pool, larger than L2, rotated between steps (no L2 reuse across steps)
+    bytes_per_set = 4 * B * C * HW * 4                       # 2 images in + 2 gradients out
+    pool_n = max(2, -(-3 * L2_BYTES // bytes_per_set))       # >= 3 x L2
+    pool_n = min(pool_n, 64)
+    sets = []
+    host_f = LossFuncRotate(None, lambda_geometric=LAMBDA_GEO)
+    host_f.init_params(None, size=S)
+    for s in range(min(pool_n, 8)):                          # 8 distinct contents are enough; more are copies
+        x, cam = poses.synthetic_batch(B, S, depth=a.depth, seed=1000 * rank + s)
+        M, c, Mi, ci = pose_algebra(host_f.K, host_f.inv_K, cam[:B], cam[B:])
+        sets.append((x, cam, np.concatenate([M.reshape(-1), c.reshape(-1), Mi.reshape(-1), ci.reshape(-1)])))
+    pool = []
+    for s in range(pool_n):
+        x, cam, pv = sets[s % len(sets)]
+        xt = torch.from_numpy(x).to(dev)
+        pool.append(dict(img=xt[:B].contiguous(), img_rot=xt[B:].contiguous(), poses=torch.from_numpy(pv).to(dev),
+                         g_img=torch.empty((B, C, S, S), device=dev), g_rot=torch.empty((B, C, S, S), device=dev),
+                         parts=torch.zeros(8, device=dev)))
+    ws = torch.empty(lib.rgbd_consistency_workspace_bytes(B, C, S, S), dtype=torch.uint8, device=dev)
+    opts = _lib.LossOpts(_lib.NORM_L1, 1, float("nan"), float("nan"), LAMBDA_GEO, B * world)
+    stream = torch.cuda.Stream(device=dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    red = torch.zeros(4, device=dev)
+
+    def ptrs(e):
+        base = e["poses"].data_ptr()
+        return [ctypes.c_void_p(e["img"].data_ptr()), ctypes.c_void_p(e["img_rot"].data_ptr())] + \
+               [ctypes.c_void_p(base + 4 * o) for o in (0, 9 * B, 12 * B, 21 * B)]
+
+    def step_fused(e):
+        _lib.call("rgbd_consistency_fwd_bwd", *ptrs(e), B, C, S, S, ctypes.byref(opts), ctypes.c_float(LAMBDA_ROTATE),
+                  ctypes.c_void_p(e["parts"].data_ptr()), None, ctypes.c_void_p(e["g_img"].data_ptr()),
+                  ctypes.c_void_p(e["g_rot"].data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp)
+
+    def step_two_pass(e):
+        _lib.call("rgbd_consistency_fwd", *ptrs(e), B, C, S, S, ctypes.byref(opts),
+                  ctypes.c_void_p(e["parts"].data_ptr()), None, None, ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp)
+        _lib.call("rgbd_consistency_bwd", *ptrs(e), B, C, S, S, ctypes.byref(opts), ctypes.c_float(LAMBDA_ROTATE), None,
+                  None, ctypes.c_void_p(e["g_img"].data_ptr()), ctypes.c_void_p(e["g_rot"].data_ptr()),
+                  ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp)
+
+    def allreduce(e):
+        if world > 1:                     # the only collective of the path: 4 floats
+            red.copy_(e["parts"][:4], non_blocking=True)
+            dist.all_reduce(red)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(step, steps, warmup, graphs=None, sampler=None):
+        """EXACTLY `steps` steps between barrier+sync, CUDA events on the launch stream, max over ranks"""
+        with torch.cuda.stream(stream):
+            for k in range(warmup):
+                (graphs[k % pool_n].replay() if graphs else step(pool[k % pool_n]))
+                allreduce(pool[k % pool_n])
+            barrier()
+            if sampler:
+                sampler.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for k in range(steps):
+                (graphs[k % pool_n].replay() if graphs else step(pool[k % pool_n]))
+                allreduce(pool[k % pool_n])
+            e1.record(stream)
+            barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def capture(step):
+        gs = []
+        with torch.cuda.stream(stream):
+            for e in pool:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    step(e)
+                gs.append(g)
+        return gs
+
+    # ---- launches per step (counted by the library) and clock pre-warm
+    with torch.cuda.stream(stream):
+        n0 = lib.rgbd_launch_count()
+        step_fused(pool[0])
+        launches_fused = lib.rgbd_launch_count() - n0
+        n0 = lib.rgbd_launch_count()
+        step_two_pass(pool[0])
+        launches_two = lib.rgbd_launch_count() - n0
+        torch.cuda.synchronize(dev)
+        t_end = time.perf_counter() + 0.3
+        k = 0
+        while time.perf_counter() < t_end:           # bring clocks up before anything is timed
+            step_fused(pool[k % pool_n]); k += 1
+        torch.cuda.synchronize(dev)
+
+    use_graph = (not a.no_graph) and world == 1
+    graphs_fused = capture(step_fused) if use_graph else None
+    graphs_two = capture(step_two_pass) if use_graph else None
+
+    sampler = ClockSampler(local)
+    ms = timed(step_fused, a.steps, a.warmup, graphs_fused, sampler)
+    clocks = sampler.stop()
+    ms_two = timed(step_two_pass, a.steps, a.warmup, graphs_two)
+    value = world * B * a.steps / (ms * 1e-3)
+    value_two = world * B * a.steps / (ms_two * 1e-3)
+
+    # ---- roofline of the dominant kernel: k_consistency<4,LOSS,GRAD> timed live with CUDA events
+    # recorded by the library around that launch (rgbd_profile_hook), same steps, same pool rotation
+    kern_ms = []
+    with torch.cuda.stream(stream):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        for k in range(a.steps):
+            lib.rgbd_profile_hook(ctypes.c_void_p(evs[k][0].cuda_event), ctypes.c_void_p(evs[k][1].cuda_event))
+            step_fused(pool[k % pool_n])
+        torch.cuda.synchronize(dev)
+        kern_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    kern_avg_ms = sum(kern_ms) / len(kern_ms)
+    alg_kernel = 16 * C * HW * B                     # reads both images once + writes both gradients once
+    alg_step = 24 * C * HW * B                       # two-pass fwd+bwd definition, per pair 24*C*HW
+    achieved = alg_kernel / (kern_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_consistency<4,LOSS,GRAD> (project+gather+residual+scatter)",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "kernel_ms": kern_avg_ms,
+                "kernel_share_of_step": kern_avg_ms * a.steps / ms,
+                "algorithmic_bytes_per_launch": alg_kernel,
+                "step": {"algorithmic_bytes": alg_step, "achieved": world * alg_step * a.steps / (ms * 1e-3) / 1e9 / world,
+                         "frac": alg_step * a.steps / (ms * 1e-3) / 1e9 / hbm_peak,
+                         "note": "whole fwd+bwd step per GPU, 24*C*H*W bytes per pair (SURVEY 8d)"}}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get("k_consistency_bytes_per_launch")
+        except Exception:            # noqa: BLE001
+            pass
+
+    # ---- e2e: public API (LossFuncRotate mirror + autograd), host buffers, H2D/D2H inside the timed region
+    f = LossFuncRotate(None, lambda_geometric=LAMBDA_GEO, grad_scale=LAMBDA_ROTATE, return_new_zp=False,
+                       process_group=dist.group.WORLD if world > 1 else None)
+    host_sets = []
+    for s in range(len(sets)):
+        x, cam, _ = sets[s]
+        host_sets.append((torch.from_numpy(x).pin_memory(), cam))
+    loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def e2e_step(k):
+        xh, cam = host_sets[k % len(host_sets)]
+        xd = xh.to(dev, non_blocking=True)                           # H2D of this step's inputs
+        img = xd[:B].requires_grad_(True)
+        img_rot = xd[B:].requires_grad_(True)
+        loss, _ = f(img, cam[:B], img_rot, cam[B:], occlusion_aware=True)
+        (loss * LAMBDA_ROTATE).backward()
+        loss_host.copy_(loss.detach(), non_blocking=False)            # D2H read of the step's result
+        return img.grad
+
+    e2e_steps = min(a.steps, 100)
+    for k in range(max(3, min(a.warmup, 5))):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * B * C * HW * 4 + 24 * B * 4,
+           "d2h_bytes_per_step": 4, "steps": e2e_steps,
+           "api": "rgbd_gan_b200.loss_functions.LossFuncRotate(grad_scale=lambda_rotate, return_new_zp=False) + backward()"}
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(a, B), l2="input pool of %d sets x %.0f MB rotated between steps (> L2)"
+                           % (pool_n, bytes_per_set / 2 ** 20), cuda_graph=bool(use_graph),
+                           path="rgbd_consistency_fwd_bwd (one-pass fwd+bwd, upstream grad = lambda_rotate)",
+                           parallelism="dp%d (pairs sharded, 4-float all-reduce)" % world),
+            "two_pass": {"value": value_two, "ms_per_step": ms_two / a.steps,
+                         "path": "rgbd_consistency_fwd + rgbd_consistency_bwd (recompute)"},
+            "e2e": e2e, "gpu_launches": int(launches_fused * a.steps),
+            "launches_per_step": {"fwd_bwd": int(launches_fused), "two_pass": int(launches_two)},
+            "roofline": roofline, "clocks": clocks,
+        }
+    return line, dict(dev=dev, world=world, rank=rank, lib=lib, hbm_peak=hbm_peak)
+
+
+def sweep(a, ctx_):
+    """cfg4 of BASELINE.json: batch 256 at 128^2 and 256^2 (single GPU): pairs/s and step-level roofline"""
+    import torch
+    from rgbd_gan_b200 import _lib, poses
+    from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
+    dev, lib = ctx_["dev"], ctx_["lib"]
+    out = []
+    for S, B in ((128, 256), (256, 256)):
+        C, HW = 4, S * S
+        x, cam = poses.synthetic_batch(B, S, depth=a.depth, seed=7)
+        hf = LossFuncRotate(None, lambda_geometric=LAMBDA_GEO)
+        hf.init_params(None, size=S)
+        M, c, Mi, ci = pose_algebra(hf.K, hf.inv_K, cam[:B], cam[B:])
+        pv = torch.from_numpy(np.concatenate([M.reshape(-1), c.reshape(-1), Mi.reshape(-1), ci.reshape(-1)])).to(dev)
+        xt = torch.from_numpy(x).to(dev)
+        n_sets = 2 if S == 128 else 1                      # one set is already > L2 (256 MB / 1 GB of traffic)
+        imgs = [(xt[:B].clone(), xt[B:].clone()) for _ in range(n_sets)]
+        g_img, g_rot = torch.empty((B, C, S, S), device=dev), torch.empty((B, C, S, S), device=dev)
+        parts = torch.zeros(8, device=dev)
+        ws = torch.empty(lib.rgbd_consistency_workspace_bytes(B, C, S, S), dtype=torch.uint8, device=dev)
+        opts = _lib.LossOpts(_lib.NORM_L1, 1, float("nan"), float("nan"), LAMBDA_GEO, B)
+        base = pv.data_ptr()
+        pp = [ctypes.c_void_p(base + 4 * o) for o in (0, 9 * B, 12 * B, 21 * B)]
+
+        def step(k):
+            im, ir = imgs[k % n_sets]
+            _lib.call("rgbd_consistency_fwd_bwd", ctypes.c_void_p(im.data_ptr()), ctypes.c_void_p(ir.data_ptr()), *pp,
+                      B, C, S, S, ctypes.byref(opts), ctypes.c_float(LAMBDA_ROTATE), ctypes.c_void_p(parts.data_ptr()),
+                      None, ctypes.c_void_p(g_img.data_ptr()), ctypes.c_void_p(g_rot.data_ptr()),
+                      ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        for k in range(3):
+            step(k)
+        torch.cuda.synchronize(dev)
+        n = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(n):
+            step(k)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / n
+        gbs = 24 * C * HW * B / (ms * 1e-3) / 1e9
+        out.append({"pairs": B, "size": S, "pairs_per_s": B / (ms * 1e-3), "ms_per_step": ms,
+                    "step_algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / ctx_["hbm_peak"]})
+        del imgs, g_img, g_rot, ws, xt
+        torch.cuda.empty_cache()
+    return out
+
+
+def cpu_baseline_leg(a):
+    """rank 0, N=1 only: bounded sample (~10-20 s) of the same workload on the host cores"""
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    t0 = time.perf_counter()
+    v1 = 4 * 3 / _cpu_worker((4, a.size, a.depth, 0, 3))                       # single process, 1 core
+    value, _, procs = cpu_port_throughput(a.size, a.depth, steps=3, warmup=1, sample_pairs=4)
+    return {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "single_core_value": v1,
+            "sample": "oracle/numpy_port.py fwd+bwd (NumPy port of the Chainer CPU path), %d processes x 4 pairs x 3 "
+                      "steps at %dx%d, occlusion on; wall %.1f s" % (procs, a.size, a.size, time.perf_counter() - t0)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=32)
+    ap.add_argument("--size", type=int, default=128)
+    ap.add_argument("--depth", default="rough", choices=["rough", "smooth"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    line, ctx_ = run_ours(a)
+    if ctx_["world"] > 1:
+        import torch.distributed as dist
+        if line is not None:
+            print(json.dumps(line), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+    if not a.no_sweep:
+        line["sweep"] = sweep(a, ctx_)
+    if not a.no_cpu:
+        line["cpu_baseline"] = cpu_baseline_leg(a)
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,14 @@ extern "C" {
 RGBD_API int rgbd_version(void);
 RGBD_API const char *rgbd_last_error(void);
 
+/* Measurement aids (bench.py).  rgbd_launch_count: kernels this library has launched in this
+ * process so far.  rgbd_profile_hook: the next rgbd_consistency_* call on this host thread
+ * records ev_start / ev_stop (cudaEvent_t, caller-owned) on its stream immediately before and
+ * after its main kernel (the projection + gather + scatter kernel of the first chunk), then
+ * clears the hook.                                                                          */
+RGBD_API unsigned long long rgbd_launch_count(void);
+RGBD_API void rgbd_profile_hook(void *ev_start, void *ev_stop);
+
 /* Options of LossFuncRotate.__call__ (common/loss_functions.py:63-64) + __init__ (:32-37). */
 typedef struct {
     int norm;             /* RGBD_NORM_L1 | RGBD_NORM_L2                                  */

@@ -38,6 +38,8 @@ class DvParams(ctypes.Structure):
 SIGNATURES = {
     "rgbd_version": (c_int, []),
     "rgbd_last_error": (ctypes.c_char_p, []),
+    "rgbd_launch_count": (ctypes.c_ulonglong, []),
+    "rgbd_profile_hook": (None, [c_void, c_void]),
     "rgbd_consistency_workspace_bytes": (c_size, [c_int, c_int, c_int, c_int]),
     "rgbd_consistency_fwd": (c_int, [c_void] * 6 + [c_int] * 4 + [ctypes.POINTER(LossOpts), c_void, c_void, c_void,
                                                                  c_void, c_size, c_void]),

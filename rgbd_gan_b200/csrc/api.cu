@@ -1,5 +1,7 @@
 // api.cu -- error plumbing shared by the C-ABI entry points (include/rgbdgan_b200.h).
 #include <stdarg.h>
+
+#include <atomic>
 #include <stdio.h>
 
 #include "common.cuh"
@@ -7,6 +9,10 @@
 namespace rgbd {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+thread_local cudaEvent_t g_hook_start = nullptr, g_hook_stop = nullptr;
+
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...)
 {
@@ -33,5 +39,13 @@ extern "C" {
 RGBD_API int rgbd_version(void) { return RGBD_B200_VERSION; }
 
 RGBD_API const char *rgbd_last_error(void) { return rgbd::g_err; }
+
+RGBD_API unsigned long long rgbd_launch_count(void) { return rgbd::g_launches.load(); }
+
+RGBD_API void rgbd_profile_hook(void *ev_start, void *ev_stop)
+{
+    rgbd::g_hook_start = (cudaEvent_t)ev_start;
+    rgbd::g_hook_stop = (cudaEvent_t)ev_stop;
+}
 
 }

@@ -18,6 +18,8 @@ constexpr int kThreads = 256;
 
 void set_error(const char *fmt, ...);
 int check_launch(const char *what);
+void count_launch(int n = 1);                       // bookkeeping for rgbd_launch_count()
+extern thread_local cudaEvent_t g_hook_start, g_hook_stop;   // rgbd_profile_hook()
 
 struct Pose {          // one warp direction of one pair
     float m[9];        // K R K^-1, row major

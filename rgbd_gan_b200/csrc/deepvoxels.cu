@@ -271,6 +271,7 @@ RGBD_API int rgbd_dv_compute_proj_idcs(const rgbd_dv_params *p, const float *cam
     k_dv_count<<<nblocks, kThreads, 0, st>>>(*p, cam2world, counts);
     k_dv_scan<<<1, 1024, 0, st>>>(counts, nblocks, offsets, total);
     k_dv_compact<<<nblocks, kThreads, 0, st>>>(*p, cam2world, offsets, lin_ind, voxel_coords, n);
+    count_launch(3);
     int rc = check_launch("rgbd_dv_compute_proj_idcs");
     if (rc) return rc;
     cudaError_t e = cudaMemcpyAsync(M_host, total, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -293,6 +294,7 @@ RGBD_API int rgbd_dv_trilinear_fwd(const float *grid, const int32_t *lin_ind, co
     if (M > 0)
         k_dv_trilinear_fwd<<<(M + kThreads - 1) / kThreads, kThreads, 0, st>>>(grid, lin_ind, voxel_coords, ld, M, F,
                                                                                p->G, n, frustum);
+    count_launch();
     return check_launch("rgbd_dv_trilinear_fwd");
 }
 
@@ -311,6 +313,7 @@ RGBD_API int rgbd_dv_trilinear_bwd(const float *g_frustum, const int32_t *lin_in
     if (M > 0)
         k_dv_trilinear_bwd<<<(M + kThreads - 1) / kThreads, kThreads, 0, st>>>(g_frustum, lin_ind, voxel_coords, ld, M,
                                                                                F, p->G, n, g_grid);
+    count_launch();
     return check_launch("rgbd_dv_trilinear_bwd");
 }
 
@@ -324,6 +327,7 @@ RGBD_API int rgbd_dv_project_fwd(const rgbd_dv_params *p, const float *grid, con
     const int n = p->W * p->H * p->D;
     dim3 grid_dim((n + kThreads - 1) / kThreads, B);
     k_dv_project_fwd<<<grid_dim, kThreads, 0, (cudaStream_t)stream>>>(*p, grid, cam2world, F, frustum);
+    count_launch();
     return check_launch("rgbd_dv_project_fwd");
 }
 
@@ -341,6 +345,7 @@ RGBD_API int rgbd_dv_project_bwd(const rgbd_dv_params *p, const float *g_frustum
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
     dim3 grid_dim((n + kThreads - 1) / kThreads, B);
     k_dv_project_bwd<<<grid_dim, kThreads, 0, st>>>(*p, g_frustum, cam2world, F, g_grid);
+    count_launch();
     return check_launch("rgbd_dv_project_bwd");
 }
 
