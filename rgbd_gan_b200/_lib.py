@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librgbdgan_b200.so")
+LIB_PATH = os.environ.get("RGBD_B200_LIB") or os.path.join(_HERE, "lib", "librgbdgan_b200.so")   # env: tuning variants
 
 c_void = ctypes.c_void_p
 c_int = ctypes.c_int

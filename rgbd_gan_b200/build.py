@@ -39,18 +39,20 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """`defines`/`out` build a tuning variant (e.g. defines=["RGBD_KPIX=2"], out="lib/variants/kpix2.so")"""
+    out = out or LIB_PATH
+    if not force and out == LIB_PATH and not stale():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + \
+          ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode:
         raise RuntimeError("nvcc failed (%d): %s" % (res.returncode, " ".join(cmd)))
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
