@@ -190,12 +190,16 @@ def run_ours(a):
         xt = torch.from_numpy(x).to(dev)
         pool.append(dict(img=xt[:B].contiguous(), img_rot=xt[B:].contiguous(), poses=torch.from_numpy(pv).to(dev),
                          g_img=torch.empty((B, C, S, S), device=dev), g_rot=torch.empty((B, C, S, S), device=dev),
-                         parts=torch.zeros(8, device=dev)))
+                         parts=torch.zeros(8, device=dev), red=torch.zeros(4, device=dev)))
     ws = torch.empty(lib.rgbd_consistency_workspace_bytes(B, C, S, S), dtype=torch.uint8, device=dev)
-    opts = _lib.LossOpts(_lib.NORM_L1, 1, float("nan"), float("nan"), LAMBDA_GEO, B * world)
+    peer = None
+    if world > 1 and a.collective == "peer":
+        from rgbd_gan_b200.distributed import PeerComm
+        peer = PeerComm()                 # fused 16-byte all-reduce inside the loss kernel (NVLink peer memory)
+    opts = _lib.LossOpts(_lib.NORM_L1, 1, float("nan"), float("nan"), LAMBDA_GEO, B * world,
+                         peer.handle if peer is not None else None)
     stream = torch.cuda.Stream(device=dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
-    red = torch.zeros(4, device=dev)
 
     def ptrs(e):
         base = e["poses"].data_ptr()
@@ -214,10 +218,26 @@ def run_ours(a):
                   None, ctypes.c_void_p(e["g_img"].data_ptr()), ctypes.c_void_p(e["g_rot"].data_ptr()),
                   ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp)
 
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+
     def allreduce(e):
-        if world > 1:                     # the only collective of the path: 4 floats
-            red.copy_(e["parts"][:4], non_blocking=True)
-            dist.all_reduce(red)
+        """the only collective of the path: all-reduce(sum) of the 4 loss means.  The gradients do not
+        depend on it (denominators are global by construction), so it runs on a side stream and overlaps
+        the next step's kernels; the timed region ends with both streams drained."""
+        if world == 1 or peer is not None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            e["red"].copy_(e["parts"][:4], non_blocking=True)
+            dist.all_reduce(e["red"])
+            e["comm_done"] = torch.cuda.Event()
+            e["comm_done"].record(comm)
+
+    def before_reuse(e):
+        if world > 1 and e.get("comm_done") is not None:
+            stream.wait_event(e["comm_done"])          # slot's previous all-reduce has consumed `parts`
 
     def barrier():
         if world > 1:
@@ -228,16 +248,22 @@ def run_ours(a):
         """EXACTLY `steps` steps between barrier+sync, CUDA events on the launch stream, max over ranks"""
         with torch.cuda.stream(stream):
             for k in range(warmup):
+                before_reuse(pool[k % pool_n])
                 (graphs[k % pool_n].replay() if graphs else step(pool[k % pool_n]))
                 allreduce(pool[k % pool_n])
+            if comm is not None:
+                stream.wait_stream(comm)
             barrier()
             if sampler:
                 sampler.start()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for k in range(steps):
+                before_reuse(pool[k % pool_n])
                 (graphs[k % pool_n].replay() if graphs else step(pool[k % pool_n]))
                 allreduce(pool[k % pool_n])
+            if comm is not None:
+                stream.wait_stream(comm)               # the last all-reduces are inside the timed region
             e1.record(stream)
             barrier()
         ms = e0.elapsed_time(e1)
@@ -266,13 +292,11 @@ def run_ours(a):
         step_two_pass(pool[0])
         launches_two = lib.rgbd_launch_count() - n0
         torch.cuda.synchronize(dev)
-        t_end = time.perf_counter() + 0.3
-        k = 0
-        while time.perf_counter() < t_end:           # bring clocks up before anything is timed
-            step_fused(pool[k % pool_n]); k += 1
+        for k in range(4000):                        # bring clocks up before anything is timed (fixed count:
+            step_fused(pool[k % pool_n])             # every rank must make the same sequence of loss calls)
         torch.cuda.synchronize(dev)
 
-    use_graph = (not a.no_graph) and world == 1
+    use_graph = not a.no_graph
     graphs_fused = capture(step_fused) if use_graph else None
     graphs_two = capture(step_two_pass) if use_graph else None
 
@@ -324,7 +348,7 @@ def run_ours(a):
 
     # ---- e2e: public API (LossFuncRotate mirror + autograd), host buffers, H2D/D2H inside the timed region
     f = LossFuncRotate(None, lambda_geometric=LAMBDA_GEO, grad_scale=LAMBDA_ROTATE, return_new_zp=False,
-                       process_group=dist.group.WORLD if world > 1 else None)
+                       process_group=dist.group.WORLD if (world > 1 and peer is None) else None, peer_comm=peer)
     host_sets = []
     for s in range(len(sets)):
         x, cam, _ = sets[s]
@@ -367,13 +391,17 @@ def run_ours(a):
             "config": dict(workload_config(a, B), l2="input pool of %d sets x %.0f MB rotated between steps (> L2)"
                            % (pool_n, bytes_per_set / 2 ** 20), cuda_graph=bool(use_graph),
                            path="rgbd_consistency_fwd_bwd (one-pass fwd+bwd, upstream grad = lambda_rotate)",
-                           parallelism="dp%d (pairs sharded, 4-float all-reduce)" % world),
+                           parallelism="dp%d (pairs sharded; 4-float loss all-reduce: %s)" % (
+                               world, "none" if world == 1 else ("fused in the loss kernel over NVLink peer memory"
+                                                                 if peer is not None else "NCCL on a side stream"))),
             "two_pass": {"value": value_two, "ms_per_step": ms_two / a.steps,
                          "path": "rgbd_consistency_fwd + rgbd_consistency_bwd (recompute)"},
             "e2e": e2e, "gpu_launches": int(launches_fused * a.steps),
             "launches_per_step": {"fwd_bwd": int(launches_fused), "two_pass": int(launches_two)},
             "roofline": roofline, "clocks": clocks,
         }
+    if peer is not None:
+        peer.close()
     return line, dict(dev=dev, world=world, rank=rank, lib=lib, hbm_peak=hbm_peak)
 
 
@@ -426,6 +454,60 @@ def sweep(a, ctx_):
     return out
 
 
+def deepvoxels_bench(ctx_):
+    """cfg3 of BASELINE.json: DeepVoxels projection sampling fwd (frustum gather) + bwd (lift scatter).
+    Production geometry (deepvoxels_generator.py:229-253: G=32, F=32, 64x64x56, yml batch 10 -> run 16) and
+    BASELINE's 64^3 volume.  Algorithmic bytes per sample fwd+bwd = 2*(F*G^3 + F*D*H*W)*4."""
+    import torch
+    from rgbd_gan_b200 import _lib, poses
+    dev, lib = ctx_["dev"], ctx_["lib"]
+    out = []
+    for G, B in ((32, 16), (64, 16)):
+        F, img = 32, 64
+        D = int(np.ceil(np.sqrt(3) * G))
+        vs = (1. / G) * 1.1 * 0.5
+        P = _lib.DvParams(img, img, D, G, 128., 128., 32., 32., float(np.float32(vs)), float(np.float32(np.sqrt(3) / 4)))
+        np.random.seed(3)
+        thetas = poses.CameraParamPrior.from_ranges(poses.CAR_RANGES, True).sample(2 * B)[:B]
+        cam = torch.from_numpy(poses.get_camera_matries(thetas).reshape(B, 16)).to(dev)
+        n = img * img * D
+        n_sets = 3 if G == 32 else 2                     # rotate buffers: > L2 in total
+        grids = [torch.randn((B, F, G, G, G), device=dev) for _ in range(n_sets)]
+        frs = [torch.empty((B, F, n), device=dev) for _ in range(n_sets)]
+        ggs = [torch.empty((B, F, G ** 3), device=dev) for _ in range(n_sets)]
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def fwd(k):
+            _lib.call("rgbd_dv_project_fwd", ctypes.byref(P), ctypes.c_void_p(grids[k % n_sets].data_ptr()),
+                      ctypes.c_void_p(cam.data_ptr()), B, F, ctypes.c_void_p(frs[k % n_sets].data_ptr()), st)
+
+        def bwd(k):
+            _lib.call("rgbd_dv_project_bwd", ctypes.byref(P), ctypes.c_void_p(frs[k % n_sets].data_ptr()),
+                      ctypes.c_void_p(cam.data_ptr()), B, F, ctypes.c_void_p(ggs[k % n_sets].data_ptr()), st)
+
+        def timeit(fn, reps=10):
+            for k in range(3):
+                fn(k)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(reps):
+                fn(k)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / reps
+
+        ms_f, ms_b = timeit(fwd), timeit(bwd)
+        alg = 2 * (F * G ** 3 + F * n) * 4 * B
+        gbs = alg / ((ms_f + ms_b) * 1e-3) / 1e9
+        out.append({"G": G, "F": F, "frustum": [D, img, img], "batch": B, "fwd_ms": ms_f, "bwd_ms": ms_b,
+                    "samples_per_s": B / ((ms_f + ms_b) * 1e-3), "algorithmic_GBps": gbs,
+                    "frac_of_hbm_peak": gbs / ctx_["hbm_peak"]})
+        del grids, frs, ggs
+        torch.cuda.empty_cache()
+    return out
+
+
 def cpu_baseline_leg(a):
     """rank 0, N=1 only: bounded sample (~10-20 s) of the same workload on the host cores"""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
@@ -447,6 +529,7 @@ def main():
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--depth", default="rough", choices=["rough", "smooth"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--collective", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
@@ -464,6 +547,7 @@ def main():
         return
     if not a.no_sweep:
         line["sweep"] = sweep(a, ctx_)
+        line["deepvoxels"] = deepvoxels_bench(ctx_)
     if not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg(a)
     print(json.dumps(line), flush=True)

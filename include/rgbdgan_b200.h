@@ -72,6 +72,8 @@ typedef struct {
     float min_depth;      /* :129-135, NaN = None                                         */
     float lambda_geometric; /* :143-144 (only used by backward entry points)              */
     long long n_pairs_global; /* denominator pairs; 0 means "= B"                         */
+    void *peer_comm;      /* NULL, or a handle from rgbd_peer_comm_create: the loss parts are
+                             then all-reduced over the ranks inside the finalize kernel        */
 } rgbd_loss_opts;
 
 /* ---- LossFuncRotate.__call__ : common/loss_functions.py:63-146 (+ warp :171-175,
@@ -122,6 +124,21 @@ RGBD_API int rgbd_consistency_fwd_bwd(const float *img, const float *img_rot, co
  * without touching memory.  n_elems = elements per gradient tensor (multiple of 4).        */
 RGBD_API int rgbd_consistency_rescale(float *g_img, float *g_img_rot, size_t n_elems, const float *gy_dev,
                              float gy_expected, void *stream);
+
+/* ---- multi-GPU: the only exchange of the path is the sum of the four loss means over the
+ * ranks that shard the pairs (the reference's analogue is ChainerMN's pure_nccl communicator,
+ * train_rgbd.py:103-113).  Instead of a separate NCCL launch, the finalize kernel of
+ * rgbd_consistency_fwd / _fwd_bwd exchanges the 16 bytes itself over NVLink peer memory:
+ *   1. every rank: rgbd_peer_comm_create(rank, world, &comm, handle)   (allocates a 4 KB mailbox)
+ *   2. all-gather the 64-byte handles with any host-side transport (torch.distributed, MPI)
+ *   3. every rank: rgbd_peer_comm_connect(comm, all_handles (world*64 bytes, rank order))
+ *   4. set rgbd_loss_opts.peer_comm = comm and n_pairs_global = total pairs; every rank must make
+ *      the same sequence of loss calls.  loss_parts[0..4] then hold the GLOBAL values on every
+ *      rank, summed in rank order (bit-identical on all ranks and from run to run).
+ * One box only (CUDA IPC), world <= 16.                                                     */
+RGBD_API int rgbd_peer_comm_create(int rank, int world, void **comm_out, unsigned char *ipc_handle_out);
+RGBD_API int rgbd_peer_comm_connect(void *comm, const unsigned char *all_handles);
+RGBD_API int rgbd_peer_comm_destroy(void *comm);
 
 /* ---- free functions of common/loss_functions.py ------------------------------------------ */
 

@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <stdio.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -41,6 +42,65 @@ RGBD_API int rgbd_version(void) { return RGBD_B200_VERSION; }
 RGBD_API const char *rgbd_last_error(void) { return rgbd::g_err; }
 
 RGBD_API unsigned long long rgbd_launch_count(void) { return rgbd::g_launches.load(); }
+
+RGBD_API int rgbd_peer_comm_create(int rank, int world, void **comm_out, unsigned char *ipc_handle_out)
+{
+    using namespace rgbd;
+    if (!comm_out || !ipc_handle_out || world < 1 || world > kMaxPeers || rank < 0 || rank >= world) {
+        set_error("rgbd_peer_comm_create: bad arguments (rank %d world %d, max %d)", rank, world, kMaxPeers);
+        return RGBD_E_ARG;
+    }
+    rgbd_peer_comm *pc = new rgbd_peer_comm();
+    memset(pc, 0, sizeof(*pc));
+    cudaError_t e = cudaMalloc((void **)&pc->mine, sizeof(rgbd_mailbox));
+    if (e == cudaSuccess) e = cudaMemset(pc->mine, 0, sizeof(rgbd_mailbox));
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, pc->mine);
+    if (e != cudaSuccess) {
+        set_error("rgbd_peer_comm_create: %s", cudaGetErrorString(e));
+        if (pc->mine) cudaFree(pc->mine);
+        delete pc;
+        return (int)e;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(ipc_handle_out, &h, 64);
+    pc->args.rank = rank; pc->args.world = world; pc->args.box[rank] = pc->mine;
+    *comm_out = pc;
+    return 0;
+}
+
+RGBD_API int rgbd_peer_comm_connect(void *comm, const unsigned char *all_handles)
+{
+    using namespace rgbd;
+    rgbd_peer_comm *pc = (rgbd_peer_comm *)comm;
+    if (!pc || !all_handles) { set_error("rgbd_peer_comm_connect: null argument"); return RGBD_E_ARG; }
+    for (int r = 0; r < pc->args.world; ++r) {
+        if (r == pc->args.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all_handles + 64 * r, 64);
+        void *ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("rgbd_peer_comm_connect: rank %d: %s", r, cudaGetErrorString(e));
+            return (int)e;
+        }
+        pc->args.box[r] = (rgbd_mailbox *)ptr;
+    }
+    pc->connected = true;
+    return 0;
+}
+
+RGBD_API int rgbd_peer_comm_destroy(void *comm)
+{
+    using namespace rgbd;
+    rgbd_peer_comm *pc = (rgbd_peer_comm *)comm;
+    if (!pc) return 0;
+    for (int r = 0; r < pc->args.world; ++r)
+        if (r != pc->args.rank && pc->args.box[r]) cudaIpcCloseMemHandle(pc->args.box[r]);
+    if (pc->mine) cudaFree(pc->mine);
+    delete pc;
+    return 0;
+}
 
 RGBD_API void rgbd_profile_hook(void *ev_start, void *ev_stop)
 {

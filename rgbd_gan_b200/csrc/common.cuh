@@ -21,6 +21,24 @@ int check_launch(const char *what);
 void count_launch(int n = 1);                       // bookkeeping for rgbd_launch_count()
 extern thread_local cudaEvent_t g_hook_start, g_hook_stop;   // rgbd_profile_hook()
 
+// ---- peer-memory mailbox for the fused loss all-reduce (one per rank, cudaMalloc + CUDA IPC)
+constexpr int kMaxPeers = 16;
+struct rgbd_mailbox {
+    float slot[2][kMaxPeers][4];      // [epoch parity][writer rank][4 loss means]
+    unsigned flag[2][kMaxPeers];      // epoch published by each writer
+    unsigned epoch;                   // local: last completed epoch
+    unsigned pad[31];
+};
+struct PeerArgs {
+    rgbd_mailbox *box[kMaxPeers];     // box[r] = rank r's mailbox, mapped into this process
+    int rank, world;
+};
+struct rgbd_peer_comm {               // host object behind the opaque handle of the C-ABI
+    PeerArgs args;
+    rgbd_mailbox *mine;
+    bool connected;
+};
+
 struct Pose {          // one warp direction of one pair
     float m[9];        // K R K^-1, row major
     float c[3];        // subtracted vector

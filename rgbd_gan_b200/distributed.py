@@ -7,10 +7,48 @@ runs the kernels on its shard with the GLOBAL pair count baked into the denomina
 finished by one all-reduce(sum) of four floats.  The reference's analogue is ChainerMN's
 `pure_nccl` communicator (train_rgbd.py:103-113), which it uses for weight gradients only.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
+from . import _lib
 from .loss_functions import combine_loss_parts
+
+
+class PeerComm:
+    """Handle for the fused loss all-reduce over NVLink peer memory (include/rgbdgan_b200.h,
+    rgbd_peer_comm_*): the finalize kernel of the loss exchanges the 4 means itself, so a sharded
+    step issues no NCCL call at all.  One box, one process per GPU, world <= 16.
+
+        comm = PeerComm(group)                      # collective: every rank of `group`
+        f = LossFuncRotate(xp, peer_comm=comm)      # pairs sharded over the group
+    """
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        mine = ctypes.create_string_buffer(64)
+        _lib.check(lib.rgbd_peer_comm_create(self.rank, self.world, ctypes.byref(self._h), mine), "rgbd_peer_comm_create")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(mine.raw), group=group)
+        blob = b"".join(handles)
+        _lib.check(lib.rgbd_peer_comm_connect(self._h, blob), "rgbd_peer_comm_connect")
+        dist.barrier(group=group)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        if self._h:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)          # nobody may still be writing into a mailbox
+            _lib.load().rgbd_peer_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
 
 
 def shard_range(n_pairs, rank, world_size):

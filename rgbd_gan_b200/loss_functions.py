@@ -164,11 +164,15 @@ class LossFuncRotate:
       return_new_zp   -- materialise the second return value (:146).  No reference caller uses
                          it (updater.py:340 drops it); False returns None in its place.
       process_group   -- torch.distributed group over which the PAIRS are sharded; the four
-                         loss means are all-reduced (4 floats), gradients need no communication.
+                         loss means are all-reduced (4 floats, NCCL), gradients need no communication.
+      n_pairs_global  -- total number of pairs over all shards (default: local pairs x world size,
+                         i.e. equal shards).
+      peer_comm       -- rgbd_gan_b200.distributed.PeerComm: same sharding, but the 4 floats are
+                         exchanged inside the loss kernel over NVLink peer memory (no NCCL launch).
     """
 
     def __init__(self, xp=None, K=None, norm="l1", lambda_geometric=3, *, grad_scale=None, return_new_zp=True,
-                 process_group=None):
+                 process_group=None, peer_comm=None, n_pairs_global=None):
         self.xp = xp
         self.size = None
         self.K = K
@@ -179,6 +183,10 @@ class LossFuncRotate:
         self.grad_scale = None if grad_scale is None else float(grad_scale)
         self.return_new_zp = return_new_zp
         self.process_group = process_group
+        self.peer_comm = peer_comm
+        self.n_pairs_global = n_pairs_global
+        if peer_comm is not None and process_group is not None:
+            raise ValueError("give either process_group (NCCL all-reduce) or peer_comm (fused), not both")
         self.last_loss_parts = None
         self._uploader = _PoseUploader()
         self._ws = {}
@@ -216,10 +224,14 @@ class LossFuncRotate:
         if self.process_group is not None:
             import torch.distributed as dist
             world = dist.get_world_size(self.process_group)
+        peer = None
+        if self.peer_comm is not None:
+            world, peer = self.peer_comm.world, self.peer_comm.handle
         return LossOpts(_lib.NORM_L1 if self.norm == "l1" else _lib.NORM_L2, int(bool(occlusion_aware)),
                         float("nan") if max_depth is None else float(max_depth),
                         float("nan") if min_depth is None else float(min_depth),
-                        float(self.lambda_geometric), int(B) * world)
+                        float(self.lambda_geometric),
+                        int(self.n_pairs_global) if self.n_pairs_global else int(B) * world, peer)
 
     def _allreduce_combine(self, parts):
         """sum the four per-shard means over the group, then combine as :141-144 (fp32)"""
