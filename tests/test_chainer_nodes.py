@@ -1,0 +1,175 @@
+"""CPU: the Chainer FunctionNode glue (rgbd_gan_b200/chainer_nodes.py) driven through the Chainer-v7
+shim the golden generator uses, with the C-ABI replaced by a stand-in that executes each entry point
+with the CPU oracle on the very pointers it is handed.  This checks what cannot be checked on the
+GPU box (no Chainer/CuPy there either): argument order and shapes of every C-ABI call the nodes make,
+retained state, the device-scalar upstream gradient, the fused grad_scale path, and that
+`LossFuncRotate(...)(img, theta, img_rot, theta_rot)` + `loss.backward()` reproduce the reference."""
+import ctypes
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, assert_grad_close, case_options, load_golden
+
+sys.path.insert(0, GOLDEN)
+import chainer_shim  # noqa: E402
+
+
+class _Ptr:
+    def __init__(self, a):
+        self.ptr = a.ctypes.data
+
+
+class HostArr(np.ndarray):
+    """numpy array that looks like a cupy array to the glue (`.data.ptr`)"""
+
+    @property
+    def data(self):
+        return _Ptr(self)
+
+
+def _wrap(a):
+    return np.ascontiguousarray(a).view(HostArr)
+
+
+class FakeXP(types.ModuleType):
+    def __init__(self):
+        super().__init__("fake_cupy")
+        self.cuda = types.SimpleNamespace(get_current_stream=lambda: types.SimpleNamespace(ptr=0))
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+    @staticmethod
+    def asarray(a, dtype=None):
+        return _wrap(np.asarray(a, dtype=dtype))
+
+    @staticmethod
+    def ascontiguousarray(a, dtype=None):
+        return _wrap(np.ascontiguousarray(a, dtype=dtype))
+
+    @staticmethod
+    def empty(shape, dtype="float32"):
+        return _wrap(np.full(shape, np.nan if np.dtype(dtype).kind == "f" else 0, dtype=dtype))
+
+    @staticmethod
+    def zeros(shape, dtype="float32"):
+        return _wrap(np.zeros(shape, dtype=dtype))
+
+    @staticmethod
+    def empty_like(a):
+        return _wrap(np.full(a.shape, np.nan, dtype=a.dtype))
+
+
+def _view(p, shape, ctype=ctypes.c_float):
+    p = p.value if isinstance(p, ctypes.c_void_p) else p
+    if not p:
+        return None
+    n = int(np.prod(shape))
+    return np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctype)), shape=(n,)).reshape(shape)
+
+
+class OracleBackedLib:
+    """same call surface as rgbd_gan_b200._lib, every entry point executed by the CPU oracle"""
+
+    def __init__(self, oracle):
+        self.oracle, self.calls = oracle, []
+
+    def load(self):
+        return types.SimpleNamespace(rgbd_consistency_workspace_bytes=lambda B, C, H, W: 1024)
+
+    def _common(self, a):
+        img, img_rot, M, c, Mi, ci, B, C, H, W, opts = a[:11]
+        o = opts._obj
+        sh = (B, C, H, W)
+        kw = dict(norm=o.norm, occlusion=bool(o.occlusion_aware),
+                  max_depth=None if np.isnan(o.max_depth) else o.max_depth,
+                  min_depth=None if np.isnan(o.min_depth) else o.min_depth,
+                  n_pairs_global=o.n_pairs_global or B)
+        arrs = (_view(img, sh), _view(img_rot, sh), _view(M, (B, 9)), _view(c, (B, 3)), _view(Mi, (B, 9)), _view(ci, (B, 3)))
+        return arrs, (B, C, H, W), o, kw
+
+    def _fwd(self, arrs, dims, o, kw, parts, new_zp):
+        B, C, H, W = dims
+        p, d = self.oracle.consistency_fwd(*arrs, debug=True, **kw)
+        out = _view(parts, (8,))
+        out[:4] = p
+        out[4] = self.oracle.combine_loss(p, o.lambda_geometric)
+        out[5:] = 0
+        z = _view(new_zp, (2 * B, H * W, 3))
+        if z is not None:
+            z[...] = d["new_zp"]
+
+    def call(self, name, *a):
+        self.calls.append(name)
+        if name == "rgbd_consistency_fwd":
+            arrs, dims, o, kw = self._common(a)
+            assert len(a) == 17
+            self._fwd(arrs, dims, o, kw, a[11], a[12])
+        elif name == "rgbd_consistency_fwd_bwd":
+            arrs, dims, o, kw = self._common(a)
+            assert len(a) == 19
+            gy = a[11].value
+            self._fwd(arrs, dims, o, kw, a[12], a[13])
+            gi, gr = self.oracle.consistency_bwd(*arrs, lambda_geometric=o.lambda_geometric, gy=gy, **kw)
+            _view(a[14], dims)[...] = gi
+            _view(a[15], dims)[...] = gr
+        elif name == "rgbd_consistency_bwd":
+            arrs, dims, o, kw = self._common(a)
+            assert len(a) == 19
+            B, C, H, W = dims
+            gy = a[11].value * (float(_view(a[12], (1,))[0]) if a[12].value else 1.0)
+            gz = _view(a[13], (2 * B, H * W, 3))
+            gi, gr = self.oracle.consistency_bwd(*arrs, lambda_geometric=o.lambda_geometric, gy=gy, g_new_zp=gz, **kw)
+            _view(a[14], dims)[...] = gi
+            _view(a[15], dims)[...] = gr
+        elif name == "rgbd_consistency_rescale":
+            g0, g1, n, gy_dev, expected, _ = a
+            r = float(_view(gy_dev, (1,))[0]) / expected.value
+            if r != 1.0:
+                _view(g0, (n,))[...] *= r
+                _view(g1, (n,))[...] *= r
+        else:
+            raise AssertionError("unexpected C-ABI call " + name)
+
+
+@pytest.fixture()
+def nodes():
+    chainer_shim.install()
+    for m in [k for k in sys.modules if k.startswith("rgbd_gan_b200.chainer_nodes")]:
+        del sys.modules[m]
+    import rgbd_gan_b200.chainer_nodes as cn       # picks up the shim as `chainer`
+    assert cn.FunctionNode is chainer_shim.FunctionNode and not cn.HAVE_CHAINER
+    return cn
+
+
+@pytest.mark.parametrize("name", ["loss_cfg0_l1_occ", "loss_s32_l2_feat", "loss_dv_maxdepth", "loss_edge_wild"])
+@pytest.mark.parametrize("grad_scale", [None, 2.0, 0.5])
+def test_chainer_node_reproduces_reference(nodes, oracle_mod, name, grad_scale):
+    g = load_golden(name)
+    o = case_options(g)
+    B = o["B"]
+    lib = OracleBackedLib(oracle_mod)
+    f = nodes.LossFuncRotate(FakeXP(), K=None if o["K"] is None else o["K"].copy(), norm=o["norm"],
+                             lambda_geometric=o["lam"], grad_scale=grad_scale, lib=lib)
+    V = chainer_shim.Variable
+    img, img_rot = V(_wrap(g["x"][:B])), V(_wrap(g["x"][B:]))
+    kw = dict(occlusion_aware=o["occ"])
+    if o["max_depth"] is not None:
+        kw["max_depth"] = o["max_depth"]
+    if o["min_depth"] is not None:
+        kw["min_depth"] = o["min_depth"]
+    loss, zp = f(img, g["cam"][:B], img_rot, g["cam"][B:], **kw)
+    assert loss.shape == () and zp.shape == g["new_zp_cat"].shape
+    (loss * o["gy"]).backward()                      # updater.py:363-365,387
+    assert abs(float(loss.array) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    np.testing.assert_array_equal(np.asarray(zp.array), g["new_zp_cat"])
+    assert_grad_close(np.asarray(img.grad), g["g_img"])
+    assert_grad_close(np.asarray(img_rot.grad), g["g_img_rot"])
+    np.testing.assert_array_equal(f.K, g["K"])
+    expect = ["rgbd_consistency_fwd", "rgbd_consistency_bwd"] if grad_scale is None else \
+             ["rgbd_consistency_fwd_bwd", "rgbd_consistency_rescale"]
+    assert lib.calls == expect
