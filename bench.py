@@ -476,14 +476,18 @@ def deepvoxels_bench(ctx_):
         frs = [torch.empty((B, F, n), device=dev) for _ in range(n_sets)]
         ggs = [torch.empty((B, F, G ** 3), device=dev) for _ in range(n_sets)]
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        dws = torch.empty(lib.rgbd_dv_project_workspace_bytes(ctypes.byref(P), B, F), dtype=torch.uint8, device=dev)
+        wsp = ctypes.c_void_p(dws.data_ptr())
 
         def fwd(k):
             _lib.call("rgbd_dv_project_fwd", ctypes.byref(P), ctypes.c_void_p(grids[k % n_sets].data_ptr()),
-                      ctypes.c_void_p(cam.data_ptr()), B, F, ctypes.c_void_p(frs[k % n_sets].data_ptr()), st)
+                      ctypes.c_void_p(cam.data_ptr()), B, F, ctypes.c_void_p(frs[k % n_sets].data_ptr()), wsp,
+                      dws.numel(), st)
 
         def bwd(k):
             _lib.call("rgbd_dv_project_bwd", ctypes.byref(P), ctypes.c_void_p(frs[k % n_sets].data_ptr()),
-                      ctypes.c_void_p(cam.data_ptr()), B, F, ctypes.c_void_p(ggs[k % n_sets].data_ptr()), st)
+                      ctypes.c_void_p(cam.data_ptr()), B, F, ctypes.c_void_p(ggs[k % n_sets].data_ptr()), wsp,
+                      dws.numel(), st)
 
         def timeit(fn, reps=10):
             for k in range(3):

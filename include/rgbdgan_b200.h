@@ -190,11 +190,13 @@ RGBD_API int rgbd_dv_trilinear_bwd(const float *g_frustum, const int32_t *lin_in
 /* Fused batch path used by the generator forward (deepvoxels_generator.py:287-299 ->
  * deepvoxel.py:879-884): compute_proj_idcs + interpolate_trilinear per sample without the
  * index lists, the compaction or the host sync.  grid (B,F,G,G,G), cam2world (B,16),
- * frustum (B,F,D,H,W).                                                                     */
+ * frustum (B,F,D,H,W).  workspace (rgbd_dv_project_workspace_bytes) holds a channels-last copy
+ * of a chunk of grids / grid gradients; with workspace == NULL a slower planar kernel runs.   */
+RGBD_API size_t rgbd_dv_project_workspace_bytes(const rgbd_dv_params *p, int B, int F);
 RGBD_API int rgbd_dv_project_fwd(const rgbd_dv_params *p, const float *grid, const float *cam2world, int B,
-                        int F, float *frustum, void *stream);
+                        int F, float *frustum, void *workspace, size_t workspace_bytes, void *stream);
 RGBD_API int rgbd_dv_project_bwd(const rgbd_dv_params *p, const float *g_frustum, const float *cam2world,
-                        int B, int F, float *g_grid, void *stream);
+                        int B, int F, float *g_grid, void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -62,8 +62,11 @@ SIGNATURES = {
                                       c_void]),
     "rgbd_dv_trilinear_bwd": (c_int, [c_void, c_void, c_void, c_int, c_int, c_int, ctypes.POINTER(DvParams), c_void,
                                       c_void]),
-    "rgbd_dv_project_fwd": (c_int, [ctypes.POINTER(DvParams), c_void, c_void, c_int, c_int, c_void, c_void]),
-    "rgbd_dv_project_bwd": (c_int, [ctypes.POINTER(DvParams), c_void, c_void, c_int, c_int, c_void, c_void]),
+    "rgbd_dv_project_workspace_bytes": (c_size, [ctypes.POINTER(DvParams), c_int, c_int]),
+    "rgbd_dv_project_fwd": (c_int, [ctypes.POINTER(DvParams), c_void, c_void, c_int, c_int, c_void, c_void, c_size,
+                                    c_void]),
+    "rgbd_dv_project_bwd": (c_int, [ctypes.POINTER(DvParams), c_void, c_void, c_int, c_int, c_void, c_void, c_size,
+                                    c_void]),
 }
 
 _lib = None

@@ -130,6 +130,186 @@ k_dv_project_bwd(const rgbd_dv_params P, const float *__restrict__ g_frustum, co
     }
 }
 
+// ---------------------------------------------------------------- channels-last fast path (fused batch entry points)
+// The planar (B,F,G,G,G) grid makes every tap a 4-byte gather from F different planes: 8*F scattered
+// 4-byte loads (or REDs) per frustum element, ~3.5 L1 wavefronts each.  Staging the grid of a chunk of
+// samples as (B,G^3,F) in L2 turns one tap of one element into ONE 128-byte line that a warp reads (or
+// REDs) with lane = feature: 8 wavefronts per element for all 32 features.  The frustum side stays in the
+// reference's planar (F, D*H*W) layout; a 32x32 shared-memory tile per warp transposes between the two.
+
+// (B,F,G3) <-> (B,G3,F), 32x32 tiles through shared memory; block (32,8)
+__global__ void __launch_bounds__(256)
+k_dv_to_cl(const float *__restrict__ grid, float *__restrict__ cl, int F, int G3)
+{
+    __shared__ float t[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y, b = blockIdx.z;
+    const int v0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int f = f0 + ty + j, v = v0 + tx;
+        t[ty + j][tx] = (f < F && v < G3) ? __ldg(grid + ((size_t)b * F + f) * G3 + v) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int v = v0 + ty + j, f = f0 + tx;
+        if (f < F && v < G3) cl[((size_t)b * G3 + v) * F + f] = t[tx][ty + j];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_dv_from_cl(const float *__restrict__ cl, float *__restrict__ grid, int F, int G3)
+{
+    __shared__ float t[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y, b = blockIdx.z;
+    const int v0 = blockIdx.x * 32, f0 = blockIdx.y * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int v = v0 + ty + j, f = f0 + tx;
+        t[ty + j][tx] = (f < F && v < G3) ? cl[((size_t)b * G3 + v) * F + f] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int f = f0 + ty + j, v = v0 + tx;
+        if (f < F && v < G3) grid[((size_t)b * F + f) * G3 + v] = t[tx][ty + j];
+    }
+}
+
+struct ElemTaps {            // what one lane computes for its own element and then broadcasts
+    int off[8];              // voxel index * F of the 8 corners, corner order of deepvoxel.py:416-423
+    float wx0, wx1, wy0, wy1, wz0, wz1;
+};
+
+__device__ __forceinline__ void dv_elem_taps(const float vc[3], int G, int F, ElemTaps &t)
+{
+    const float X = vc[2], Y = vc[1], Z = vc[0];                 // axis swap (deepvoxel.py:394-396)
+    const int x0 = __float2int_rz(X), y0 = __float2int_rz(Y), z0 = __float2int_rz(Z);
+    const int x1 = min(max(x0 + 1, 0), G - 1), y1 = min(max(y0 + 1, 0), G - 1), z1 = min(max(z0 + 1, 0), G - 1);
+    const double fx = (double)X - (double)x0, fy = (double)Y - (double)y0, fz = (double)Z - (double)z0;
+    t.wx1 = (float)fx; t.wx0 = (float)(1.0 - fx);
+    t.wy1 = (float)fy; t.wy0 = (float)(1.0 - fy);
+    t.wz1 = (float)fz; t.wz0 = (float)(1.0 - fz);
+    // (0,0,0)(1,0,0)(0,1,0)(0,0,1)(1,0,1)(0,1,1)(1,1,0)(1,1,1)
+    t.off[0] = (x0 * G + y0) * G + z0; t.off[1] = (x1 * G + y0) * G + z0;
+    t.off[2] = (x0 * G + y1) * G + z0; t.off[3] = (x0 * G + y0) * G + z1;
+    t.off[4] = (x1 * G + y0) * G + z1; t.off[5] = (x0 * G + y1) * G + z1;
+    t.off[6] = (x1 * G + y1) * G + z0; t.off[7] = (x1 * G + y1) * G + z1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t.off[k] *= F;       // element offset of the corner's feature line in the chunk (< 2^31)
+}
+
+constexpr int kDvWarps = 8;
+
+// one warp = 32 consecutive frustum elements; lane = feature while gathering, lane = element while storing
+__global__ void __launch_bounds__(32 * kDvWarps)
+k_dv_project_fwd_cl(const rgbd_dv_params P, const float *__restrict__ cl, const float *__restrict__ cam2world,
+                    int F, float *__restrict__ frustum)
+{
+    __shared__ float tile[kDvWarps][32][33];
+    const int n = P.W * P.H * P.D;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int base = (blockIdx.x * kDvWarps + wid) * 32;
+    if (base >= n) return;
+    const int l = base + lane;
+    const Cam T = load_cam(cam2world + 16 * b);
+    float vc[3] = {0.f, 0.f, 0.f};
+    const bool keep = (l < n) && dv_coords(P, T, l, vc);
+    ElemTaps mine = {};
+    if (keep) dv_elem_taps(vc, P.G, F, mine);
+    const unsigned kept = __ballot_sync(0xffffffffu, keep);
+    const size_t G3 = (size_t)P.G * P.G * P.G;
+    float (*tl)[33] = tile[wid];
+    const unsigned FULL = 0xffffffffu;
+    for (int f0 = 0; f0 < F; f0 += 32) {
+        const int f = f0 + lane;
+        const float *__restrict__ src = cl + (size_t)b * G3 * F;
+        const int fl = f < F ? f : 0;
+#pragma unroll 4
+        for (int e = 0; e < 32; ++e) tl[e][lane] = 0.0f;               // elements outside the grid stay 0
+        for (unsigned rem = kept; rem; rem &= rem - 1) {               // warp-uniform loop over kept elements
+            const int e = __ffs(rem) - 1;
+            const float wx0 = __shfl_sync(FULL, mine.wx0, e), wx1 = __shfl_sync(FULL, mine.wx1, e);
+            const float wy0 = __shfl_sync(FULL, mine.wy0, e), wy1 = __shfl_sync(FULL, mine.wy1, e);
+            const float wz0 = __shfl_sync(FULL, mine.wz0, e), wz1 = __shfl_sync(FULL, mine.wz1, e);
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(src + (__shfl_sync(FULL, mine.off[k], e) + fl));
+            // each term ((v*wx)*wy)*wz, summed left to right in the corner order of deepvoxel.py:416-423
+#define RGBD_TERM(K_, WX_, WY_, WZ_) __fmul_rn(__fmul_rn(__fmul_rn(v[K_], WX_), WY_), WZ_)
+            float acc = RGBD_TERM(0, wx0, wy0, wz0);
+            acc = __fadd_rn(acc, RGBD_TERM(1, wx1, wy0, wz0));
+            acc = __fadd_rn(acc, RGBD_TERM(2, wx0, wy1, wz0));
+            acc = __fadd_rn(acc, RGBD_TERM(3, wx0, wy0, wz1));
+            acc = __fadd_rn(acc, RGBD_TERM(4, wx1, wy0, wz1));
+            acc = __fadd_rn(acc, RGBD_TERM(5, wx0, wy1, wz1));
+            acc = __fadd_rn(acc, RGBD_TERM(6, wx1, wy1, wz0));
+            acc = __fadd_rn(acc, RGBD_TERM(7, wx1, wy1, wz1));
+#undef RGBD_TERM
+            tl[e][lane] = acc;                                          // row = element, column = feature
+        }
+        __syncwarp();
+        if (l < n) {
+            const int fmax = min(32, F - f0);
+            float *out = frustum + ((size_t)b * F + f0) * n + l;
+            for (int ff = 0; ff < fmax; ++ff) out[(size_t)ff * n] = tl[lane][ff];   // coalesced along l
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(32 * kDvWarps)
+k_dv_project_bwd_cl(const rgbd_dv_params P, const float *__restrict__ g_frustum, const float *__restrict__ cam2world,
+                    int F, float *__restrict__ gcl)
+{
+    __shared__ float tile[kDvWarps][32][33];
+    const int n = P.W * P.H * P.D;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int base = (blockIdx.x * kDvWarps + wid) * 32;
+    if (base >= n) return;
+    const int l = base + lane;
+    const Cam T = load_cam(cam2world + 16 * b);
+    float vc[3] = {0.f, 0.f, 0.f};
+    const bool keep = (l < n) && dv_coords(P, T, l, vc);
+    ElemTaps mine = {};
+    if (keep) dv_elem_taps(vc, P.G, F, mine);
+    const unsigned kept = __ballot_sync(0xffffffffu, keep);
+    if (kept == 0u) return;
+    // the lift only needs 1e-5: fold the three factors of every corner once per element (owner lane)
+    float w[8];
+    w[0] = (mine.wz0 * mine.wy0) * mine.wx0; w[1] = (mine.wz0 * mine.wy0) * mine.wx1;
+    w[2] = (mine.wz0 * mine.wy1) * mine.wx0; w[3] = (mine.wz1 * mine.wy0) * mine.wx0;
+    w[4] = (mine.wz1 * mine.wy0) * mine.wx1; w[5] = (mine.wz1 * mine.wy1) * mine.wx0;
+    w[6] = (mine.wz0 * mine.wy1) * mine.wx1; w[7] = (mine.wz1 * mine.wy1) * mine.wx1;
+    const size_t G3 = (size_t)P.G * P.G * P.G;
+    float (*tl)[33] = tile[wid];
+    const unsigned FULL = 0xffffffffu;
+    for (int f0 = 0; f0 < F; f0 += 32) {
+        const int fmax = min(32, F - f0);
+        if (l < n) {
+            const float *go = g_frustum + ((size_t)b * F + f0) * n + l;
+            for (int ff = 0; ff < fmax; ++ff) tl[lane][ff] = __ldg(go + (size_t)ff * n);   // coalesced along l
+        }
+        __syncwarp();
+        const int f = f0 + lane;
+        float *__restrict__ dst = gcl + (size_t)b * G3 * F;
+        const int fl = f < F ? f : 0;
+        for (unsigned rem = kept; rem; rem &= rem - 1) {
+            const int e = __ffs(rem) - 1;
+            const float g = tl[e][lane];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int off = __shfl_sync(FULL, mine.off[k], e);
+                const float wk = __shfl_sync(FULL, w[k], e);
+                if (f < F) atomicAdd(dst + (off + fl), g * wk);             // one 128-byte line per corner
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------- explicit index-list path
 __global__ void __launch_bounds__(kThreads)
 k_dv_trilinear_fwd(const float *__restrict__ grid, const int32_t *__restrict__ lin_ind,
@@ -317,22 +497,55 @@ RGBD_API int rgbd_dv_trilinear_bwd(const float *g_frustum, const int32_t *lin_in
     return check_launch("rgbd_dv_trilinear_bwd");
 }
 
+static size_t dv_chunk_samples(const rgbd_dv_params *p, int B, int F)
+{
+    const size_t per = (size_t)p->G * p->G * p->G * F * sizeof(float);
+    size_t n = ((size_t)48 << 20) / per;                 // keep the channels-last copy L2-resident
+    if (n < 1) n = 1;
+    if (n > (size_t)B) n = B;
+    return n;
+}
+
+RGBD_API size_t rgbd_dv_project_workspace_bytes(const rgbd_dv_params *p, int B, int F)
+{
+    if (!dv_ok(p) || B <= 0 || F <= 0) return 0;
+    return dv_chunk_samples(p, B, F) * (size_t)p->G * p->G * p->G * F * sizeof(float);
+}
+
 RGBD_API int rgbd_dv_project_fwd(const rgbd_dv_params *p, const float *grid, const float *cam2world, int B, int F,
-                        float *frustum, void *stream)
+                        float *frustum, void *workspace, size_t workspace_bytes, void *stream)
 {
     if (!dv_ok(p) || !grid || !cam2world || !frustum || B <= 0 || F <= 0) {
         set_error("rgbd_dv_project_fwd: null pointer or bad params");
         return RGBD_E_ARG;
     }
+    cudaStream_t st = (cudaStream_t)stream;
     const int n = p->W * p->H * p->D;
-    dim3 grid_dim((n + kThreads - 1) / kThreads, B);
-    k_dv_project_fwd<<<grid_dim, kThreads, 0, (cudaStream_t)stream>>>(*p, grid, cam2world, F, frustum);
-    count_launch();
+    if (!workspace) {                                     // planar fallback: no staging memory available
+        dim3 grid_dim((n + kThreads - 1) / kThreads, B);
+        k_dv_project_fwd<<<grid_dim, kThreads, 0, st>>>(*p, grid, cam2world, F, frustum);
+        count_launch();
+        return check_launch("rgbd_dv_project_fwd");
+    }
+    if (workspace_bytes < rgbd_dv_project_workspace_bytes(p, B, F)) {
+        set_error("rgbd_dv_project_fwd: workspace too small");
+        return RGBD_E_WORKSPACE;
+    }
+    const int G3 = p->G * p->G * p->G;
+    const int Bs = (int)dv_chunk_samples(p, B, F);
+    float *cl = (float *)workspace;
+    for (int b0 = 0; b0 < B; b0 += Bs) {
+        const int nb = (B - b0 < Bs) ? (B - b0) : Bs;
+        k_dv_to_cl<<<dim3((G3 + 31) / 32, (F + 31) / 32, nb), dim3(32, 8), 0, st>>>(grid + (size_t)b0 * F * G3, cl, F, G3);
+        k_dv_project_fwd_cl<<<dim3((n + 32 * kDvWarps - 1) / (32 * kDvWarps), nb), 32 * kDvWarps, 0, st>>>(
+            *p, cl, cam2world + 16 * (size_t)b0, F, frustum + (size_t)b0 * F * n);
+        count_launch(2);
+    }
     return check_launch("rgbd_dv_project_fwd");
 }
 
 RGBD_API int rgbd_dv_project_bwd(const rgbd_dv_params *p, const float *g_frustum, const float *cam2world, int B, int F,
-                        float *g_grid, void *stream)
+                        float *g_grid, void *workspace, size_t workspace_bytes, void *stream)
 {
     if (!dv_ok(p) || !g_frustum || !cam2world || !g_grid || B <= 0 || F <= 0) {
         set_error("rgbd_dv_project_bwd: null pointer or bad params");
@@ -341,11 +554,29 @@ RGBD_API int rgbd_dv_project_bwd(const rgbd_dv_params *p, const float *g_frustum
     cudaStream_t st = (cudaStream_t)stream;
     const int n = p->W * p->H * p->D;
     const size_t G3 = (size_t)p->G * p->G * p->G;
-    cudaError_t e = cudaMemsetAsync(g_grid, 0, sizeof(float) * (size_t)B * F * G3, st);
-    if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
-    dim3 grid_dim((n + kThreads - 1) / kThreads, B);
-    k_dv_project_bwd<<<grid_dim, kThreads, 0, st>>>(*p, g_frustum, cam2world, F, g_grid);
-    count_launch();
+    if (!workspace) {
+        cudaError_t e = cudaMemsetAsync(g_grid, 0, sizeof(float) * (size_t)B * F * G3, st);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        dim3 grid_dim((n + kThreads - 1) / kThreads, B);
+        k_dv_project_bwd<<<grid_dim, kThreads, 0, st>>>(*p, g_frustum, cam2world, F, g_grid);
+        count_launch();
+        return check_launch("rgbd_dv_project_bwd");
+    }
+    if (workspace_bytes < rgbd_dv_project_workspace_bytes(p, B, F)) {
+        set_error("rgbd_dv_project_bwd: workspace too small");
+        return RGBD_E_WORKSPACE;
+    }
+    const int Bs = (int)dv_chunk_samples(p, B, F);
+    float *gcl = (float *)workspace;
+    for (int b0 = 0; b0 < B; b0 += Bs) {
+        const int nb = (B - b0 < Bs) ? (B - b0) : Bs;
+        cudaError_t e = cudaMemsetAsync(gcl, 0, sizeof(float) * (size_t)nb * F * G3, st);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        k_dv_project_bwd_cl<<<dim3((n + 32 * kDvWarps - 1) / (32 * kDvWarps), nb), 32 * kDvWarps, 0, st>>>(
+            *p, g_frustum + (size_t)b0 * F * n, cam2world + 16 * (size_t)b0, F, gcl);
+        k_dv_from_cl<<<dim3(((int)G3 + 31) / 32, (F + 31) / 32, nb), dim3(32, 8), 0, st>>>(gcl, g_grid + (size_t)b0 * F * G3, F, (int)G3);
+        count_launch(2);
+    }
     return check_launch("rgbd_dv_project_bwd");
 }
 

@@ -24,12 +24,19 @@ def _cam_to_device(cam2world, device):
     return torch.from_numpy(a).to(device)
 
 
+def _project_ws(params, B, F, device):
+    nbytes = _lib.load().rgbd_dv_project_workspace_bytes(ctypes.byref(params), B, F)
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
 class _ProjectFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, grid, cam, params):
         B, F = grid.shape[:2]
         out = torch.empty((B, F, params.D, params.H, params.W), dtype=torch.float32, device=grid.device)
-        _lib.call("rgbd_dv_project_fwd", ctypes.byref(params), _ptr(grid), _ptr(cam), B, F, _ptr(out), _stream())
+        ws = _project_ws(params, B, F, grid.device)          # channels-last staging copy of a chunk of grids
+        _lib.call("rgbd_dv_project_fwd", ctypes.byref(params), _ptr(grid), _ptr(cam), B, F, _ptr(out), _ptr(ws),
+                  ws.numel(), _stream())
         ctx.cam, ctx.params, ctx.gshape = cam, params, grid.shape
         return out
 
@@ -38,8 +45,9 @@ class _ProjectFn(torch.autograd.Function):
         B, F = ctx.gshape[:2]
         g_out = g_out.to(torch.float32).contiguous()
         g_grid = torch.empty(ctx.gshape, dtype=torch.float32, device=g_out.device)
+        ws = _project_ws(ctx.params, B, F, g_out.device)
         _lib.call("rgbd_dv_project_bwd", ctypes.byref(ctx.params), _ptr(g_out), _ptr(ctx.cam), B, F, _ptr(g_grid),
-                  _stream())
+                  _ptr(ws), ws.numel(), _stream())
         return g_grid, None, None
 
 

@@ -55,16 +55,21 @@ def test_projection_against_reference_golden(name):
         ggrid = torch.full((F, G3), float("nan"), device=DEV)
         _lib.call("rgbd_dv_trilinear_bwd", p(gout), p(lin), p(vc), n, M, F, ctypes.byref(P), p(ggrid), stream())
         assert_grad_close(ggrid.cpu().numpy().reshape(g["g_grid_%d" % i][0].shape), g["g_grid_%d" % i][0])
-    # fused batch path
+    # fused batch path: channels-last fast path (with workspace) and planar fallback (without)
     grid, cam, gout = dev(g["grid"]), dev(g["cam"].reshape(ns, 16)), dev(g["g_out"])
-    out = torch.full((ns, F, n), float("nan"), device=DEV)
-    _lib.call("rgbd_dv_project_fwd", ctypes.byref(P), p(grid), p(cam), ns, F, p(out), stream())
-    ggrid = torch.full((ns, F, G3), float("nan"), device=DEV)
-    _lib.call("rgbd_dv_project_bwd", ctypes.byref(P), p(gout), p(cam), ns, F, p(ggrid), stream())
-    out, ggrid = out.cpu().numpy(), ggrid.cpu().numpy()
-    for i in range(ns):
-        np.testing.assert_array_equal(out[i].reshape(g["frustum_%d" % i][0].shape), g["frustum_%d" % i][0])
-        assert_grad_close(ggrid[i].reshape(g["g_grid_%d" % i][0].shape), g["g_grid_%d" % i][0])
+    nbytes = _lib.load().rgbd_dv_project_workspace_bytes(ctypes.byref(P), ns, F)
+    assert nbytes >= G3 * F * 4
+    for ws in (torch.empty(nbytes, dtype=torch.uint8, device=DEV), None):
+        out = torch.full((ns, F, n), float("nan"), device=DEV)
+        _lib.call("rgbd_dv_project_fwd", ctypes.byref(P), p(grid), p(cam), ns, F, p(out), p(ws),
+                  0 if ws is None else ws.numel(), stream())
+        ggrid = torch.full((ns, F, G3), float("nan"), device=DEV)
+        _lib.call("rgbd_dv_project_bwd", ctypes.byref(P), p(gout), p(cam), ns, F, p(ggrid), p(ws),
+                  0 if ws is None else ws.numel(), stream())
+        out, ggrid = out.cpu().numpy(), ggrid.cpu().numpy()
+        for i in range(ns):
+            np.testing.assert_array_equal(out[i].reshape(g["frustum_%d" % i][0].shape), g["frustum_%d" % i][0])
+            assert_grad_close(ggrid[i].reshape(g["g_grid_%d" % i][0].shape), g["g_grid_%d" % i][0])
 
 
 @pytest.mark.parametrize("G,F,B", [(32, 32, 4), (64, 32, 2)])
@@ -87,12 +92,15 @@ def test_full_size_against_oracle(G, F, B, oracle_mod):
     P = DvParams(img, img, D, G, 128., 128., 32., 32., float(np.float32(vs)), float(np.float32(np.sqrt(3) / 4)))
     n = img * img * D
     out = torch.empty((B, F, n), device=DEV)
-    _lib.call("rgbd_dv_project_fwd", ctypes.byref(P), p(dev(grid)), p(dev(cam.reshape(B, 16))), B, F, p(out), stream())
+    ws = torch.empty(_lib.load().rgbd_dv_project_workspace_bytes(ctypes.byref(P), B, F), dtype=torch.uint8, device=DEV)
+    _lib.call("rgbd_dv_project_fwd", ctypes.byref(P), p(dev(grid)), p(dev(cam.reshape(B, 16))), B, F, p(out), p(ws),
+              ws.numel(), stream())
     np.testing.assert_array_equal(out.cpu().numpy().reshape(ref.shape), ref)
     g_out = rng.normal(size=ref.shape).astype(np.float32)
     ref_g = oracle_mod.dv_project_bwd(P0, g_out, cam)
     gg = torch.empty((B, F, G ** 3), device=DEV)
-    _lib.call("rgbd_dv_project_bwd", ctypes.byref(P), p(dev(g_out)), p(dev(cam.reshape(B, 16))), B, F, p(gg), stream())
+    _lib.call("rgbd_dv_project_bwd", ctypes.byref(P), p(dev(g_out)), p(dev(cam.reshape(B, 16))), B, F, p(gg), p(ws),
+              ws.numel(), stream())
     assert_grad_close(gg.cpu().numpy().reshape(ref_g.shape), ref_g)
     # adjointness <frustum(grid), g_out> == <grid, lift(g_out)> : a size-independent property of the pair
     lhs = float((ref.astype(np.float64) * g_out).sum())
