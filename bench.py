@@ -355,23 +355,42 @@ def run_ours(a):
         host_sets.append((torch.from_numpy(x).pin_memory(), cam))
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
 
-    def e2e_step(k):
-        xh, cam = host_sets[k % len(host_sets)]
-        xd = xh.to(dev, non_blocking=True)                           # H2D of this step's inputs
-        img = xd[:B].requires_grad_(True)
-        img_rot = xd[B:].requires_grad_(True)
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_in = [torch.empty((2 * B, C, S, S), device=dev) for _ in range(2)]     # double-buffered device inputs
+    in_ready = [None, None]
+
+    def h2d(k):
+        """H2D of step k's inputs (pinned -> device) on the copy stream: overlaps step k-1's kernels"""
+        xh, _ = host_sets[k % len(host_sets)]
+        with torch.cuda.stream(copy_stream):
+            dev_in[k % 2].copy_(xh, non_blocking=True)
+            in_ready[k % 2] = torch.cuda.Event()
+            in_ready[k % 2].record(copy_stream)
+
+    def e2e_step(k, last):
+        _, cam = host_sets[k % len(host_sets)]
+        torch.cuda.current_stream().wait_event(in_ready[k % 2])
+        if not last:
+            h2d(k + 1)                                                   # next step's copy is in flight during this step
+        xd = dev_in[k % 2]
+        img = xd[:B].detach().requires_grad_(True)
+        img_rot = xd[B:].detach().requires_grad_(True)
         loss, _ = f(img, cam[:B], img_rot, cam[B:], occlusion_aware=True)
         (loss * LAMBDA_ROTATE).backward()
-        loss_host.copy_(loss.detach(), non_blocking=False)            # D2H read of the step's result
+        loss_host.copy_(loss.detach(), non_blocking=False)               # D2H read of the step's result (blocks)
         return img.grad
 
     e2e_steps = min(a.steps, 100)
-    for k in range(max(3, min(a.warmup, 5))):
-        e2e_step(k)
+    nw = max(3, min(a.warmup, 5))
+    h2d(0)
+    for k in range(nw):
+        e2e_step(k, False)
+    torch.cuda.synchronize(dev)
     barrier()
     t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_step(k)
+    h2d(nw)                      # (the copy issued by the last warm-up step is repeated inside the timed region)
+    for k in range(nw, nw + e2e_steps):
+        e2e_step(k, k == nw + e2e_steps - 1)
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     if world > 1:
@@ -380,6 +399,7 @@ def run_ours(a):
         dt = float(t.item())
     e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * B * C * HW * 4 + 24 * B * 4,
            "d2h_bytes_per_step": 4, "steps": e2e_steps,
+           "pipeline": "step k+1's H2D (copy stream, double-buffered) overlaps step k's kernels; loss read back every step",
            "api": "rgbd_gan_b200.loss_functions.LossFuncRotate(grad_scale=lambda_rotate, return_new_zp=False) + backward()"}
 
     line = None
