@@ -425,14 +425,15 @@ def run_ours(a):
     return line, dict(dev=dev, world=world, rank=rank, lib=lib, hbm_peak=hbm_peak)
 
 
-def sweep(a, ctx_):
-    """cfg4 of BASELINE.json: batch 256 at 128^2 and 256^2 (single GPU): pairs/s and step-level roofline"""
+def sweep(a, ctx_, sizes=((128, 256), (256, 256)), graph_like=False):
+    """cfg4 of BASELINE.json: batch 256 at 128^2 and 256^2 (single GPU): pairs/s and step-level roofline.
+    Also used for the generator-like smooth-depth variant of the headline workload."""
     import torch
     from rgbd_gan_b200 import _lib, poses
     from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
     dev, lib = ctx_["dev"], ctx_["lib"]
     out = []
-    for S, B in ((128, 256), (256, 256)):
+    for S, B in sizes:
         C, HW = 4, S * S
         x, cam = poses.synthetic_batch(B, S, depth=a.depth, seed=7)
         hf = LossFuncRotate(None, lambda_geometric=LAMBDA_GEO)
@@ -440,12 +441,12 @@ def sweep(a, ctx_):
         M, c, Mi, ci = pose_algebra(hf.K, hf.inv_K, cam[:B], cam[B:])
         pv = torch.from_numpy(np.concatenate([M.reshape(-1), c.reshape(-1), Mi.reshape(-1), ci.reshape(-1)])).to(dev)
         xt = torch.from_numpy(x).to(dev)
-        n_sets = 2 if S == 128 else 1                      # one set is already > L2 (256 MB / 1 GB of traffic)
+        n_sets = max(1, min(16, -(-3 * L2_BYTES // (4 * B * C * HW * 4))))      # rotate > 3 x L2 of in+out data
         imgs = [(xt[:B].clone(), xt[B:].clone()) for _ in range(n_sets)]
         g_img, g_rot = torch.empty((B, C, S, S), device=dev), torch.empty((B, C, S, S), device=dev)
         parts = torch.zeros(8, device=dev)
         ws = torch.empty(lib.rgbd_consistency_workspace_bytes(B, C, S, S), dtype=torch.uint8, device=dev)
-        opts = _lib.LossOpts(_lib.NORM_L1, 1, float("nan"), float("nan"), LAMBDA_GEO, B)
+        opts = _lib.LossOpts(_lib.NORM_L1, 1, float("nan"), float("nan"), LAMBDA_GEO, B, None)
         base = pv.data_ptr()
         pp = [ctypes.c_void_p(base + 4 * o) for o in (0, 9 * B, 12 * B, 21 * B)]
 
@@ -458,7 +459,10 @@ def sweep(a, ctx_):
         for k in range(3):
             step(k)
         torch.cuda.synchronize(dev)
-        n = 20
+        n = 20 if B >= 128 else 200
+        for k in range(n_sets):
+            step(k)
+        torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for k in range(n):
@@ -467,7 +471,7 @@ def sweep(a, ctx_):
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / n
         gbs = 24 * C * HW * B / (ms * 1e-3) / 1e9
-        out.append({"pairs": B, "size": S, "pairs_per_s": B / (ms * 1e-3), "ms_per_step": ms,
+        out.append({"pairs": B, "size": S, "depth": a.depth, "pairs_per_s": B / (ms * 1e-3), "ms_per_step": ms,
                     "step_algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / ctx_["hbm_peak"]})
         del imgs, g_img, g_rot, ws, xt
         torch.cuda.empty_cache()
@@ -571,6 +575,10 @@ def main():
         return
     if not a.no_sweep:
         line["sweep"] = sweep(a, ctx_)
+        if a.depth == "rough":
+            a2 = argparse.Namespace(**vars(a))
+            a2.depth = "smooth"
+            line["smooth_depth"] = sweep(a2, ctx_, sizes=((a.size, a.pairs),), graph_like=False)[0]
         line["deepvoxels"] = deepvoxels_bench(ctx_)
     if not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg(a)
