@@ -540,10 +540,10 @@ def cpu_baseline_leg(a):
     """rank 0, N=1 only: bounded sample (~10-20 s) of the same workload on the host cores"""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     t0 = time.perf_counter()
-    v1 = 4 * 3 / _cpu_worker((4, a.size, a.depth, 0, 3))                       # single process, 1 core
-    value, _, procs = cpu_port_throughput(a.size, a.depth, steps=3, warmup=1, sample_pairs=4)
+    v1 = 4 * 6 / _cpu_worker((4, a.size, a.depth, 0, 6))                       # single process, 1 core
+    value, _, procs = cpu_port_throughput(a.size, a.depth, steps=20, warmup=1, sample_pairs=4)
     return {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "single_core_value": v1,
-            "sample": "oracle/numpy_port.py fwd+bwd (NumPy port of the Chainer CPU path), %d processes x 4 pairs x 3 "
+            "sample": "oracle/numpy_port.py fwd+bwd (NumPy port of the Chainer CPU path), %d processes x 4 pairs x 20 "
                       "steps at %dx%d, occlusion on; wall %.1f s" % (procs, a.size, a.size, time.perf_counter() - t0)}
 
 
