@@ -196,8 +196,10 @@ def run_ours(a):
     if world > 1 and a.collective == "peer":
         from rgbd_gan_b200.distributed import PeerComm
         peer = PeerComm()                 # fused 16-byte all-reduce inside the loss kernel (NVLink peer memory)
+    # N > 1: the loss exchange is deferred (joined once at the end of the timed region, inside it), so it
+    # overlaps the stage-out of its step and the stage-in of the next; gradients are never deferred
     opts = _lib.LossOpts(_lib.NORM_L1, 1, float("nan"), float("nan"), LAMBDA_GEO, B * world,
-                         peer.handle if peer is not None else None)
+                         peer.handle if peer is not None else None, 1 if peer is not None else 0, 0)
     stream = torch.cuda.Stream(device=dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
 
@@ -264,6 +266,8 @@ def run_ours(a):
                 allreduce(pool[k % pool_n])
             if comm is not None:
                 stream.wait_stream(comm)               # the last all-reduces are inside the timed region
+            if peer is not None:
+                _lib.check(lib.rgbd_peer_comm_wait(peer.handle, sp), "rgbd_peer_comm_wait")   # join the last exchange
             e1.record(stream)
             barrier()
         ms = e0.elapsed_time(e1)
@@ -296,7 +300,7 @@ def run_ours(a):
             step_fused(pool[k % pool_n])             # every rank must make the same sequence of loss calls)
         torch.cuda.synchronize(dev)
 
-    use_graph = not a.no_graph
+    use_graph = (not a.no_graph) and peer is None      # a deferred exchange cannot live inside a stream capture
     graphs_fused = capture(step_fused) if use_graph else None
     graphs_two = capture(step_two_pass) if use_graph else None
 
@@ -412,7 +416,7 @@ def run_ours(a):
                            % (pool_n, bytes_per_set / 2 ** 20), cuda_graph=bool(use_graph),
                            path="rgbd_consistency_fwd_bwd (one-pass fwd+bwd, upstream grad = lambda_rotate)",
                            parallelism="dp%d (pairs sharded; 4-float loss all-reduce: %s)" % (
-                               world, "none" if world == 1 else ("fused in the loss kernel over NVLink peer memory"
+                               world, "none" if world == 1 else ("own finalize kernel exchanges them over NVLink peer memory on a side stream, joined at the end of the timed region"
                                                                  if peer is not None else "NCCL on a side stream"))),
             "two_pass": {"value": value_two, "ms_per_step": ms_two / a.steps,
                          "path": "rgbd_consistency_fwd + rgbd_consistency_bwd (recompute)"},

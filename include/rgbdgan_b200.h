@@ -74,6 +74,12 @@ typedef struct {
     long long n_pairs_global; /* denominator pairs; 0 means "= B"                         */
     void *peer_comm;      /* NULL, or a handle from rgbd_peer_comm_create: the loss parts are
                              then all-reduced over the ranks inside the finalize kernel        */
+    int defer_loss;       /* with peer_comm: 1 = do not make `stream` wait for the exchange; the
+                             gradients are ordered on `stream` as usual, loss_parts become valid
+                             after rgbd_peer_comm_wait(comm, stream) (or the next loss call on this
+                             comm).  The exchange then overlaps the stage-out of this call and the
+                             stage-in of the next one.  Not usable under CUDA-graph stream capture. */
+    int reserved;
 } rgbd_loss_opts;
 
 /* ---- LossFuncRotate.__call__ : common/loss_functions.py:63-146 (+ warp :171-175,
@@ -139,6 +145,8 @@ RGBD_API int rgbd_consistency_rescale(float *g_img, float *g_img_rot, size_t n_e
 RGBD_API int rgbd_peer_comm_create(int rank, int world, void **comm_out, unsigned char *ipc_handle_out);
 RGBD_API int rgbd_peer_comm_connect(void *comm, const unsigned char *all_handles);
 RGBD_API int rgbd_peer_comm_destroy(void *comm);
+/* make `stream` wait for the most recent (deferred) loss exchange of this comm */
+RGBD_API int rgbd_peer_comm_wait(void *comm, void *stream);
 
 /* ---- free functions of common/loss_functions.py ------------------------------------------ */
 

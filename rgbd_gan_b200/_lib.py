@@ -24,7 +24,8 @@ class RgbdB200Error(RuntimeError):
 class LossOpts(ctypes.Structure):
     """rgbd_loss_opts"""
     _fields_ = [("norm", c_int), ("occlusion_aware", c_int), ("max_depth", c_float), ("min_depth", c_float),
-                ("lambda_geometric", c_float), ("n_pairs_global", ctypes.c_longlong), ("peer_comm", c_void)]
+                ("lambda_geometric", c_float), ("n_pairs_global", ctypes.c_longlong), ("peer_comm", c_void),
+                ("defer_loss", c_int), ("reserved", c_int)]
 
 
 class DvParams(ctypes.Structure):
@@ -43,6 +44,7 @@ SIGNATURES = {
     "rgbd_peer_comm_create": (c_int, [c_int, c_int, ctypes.POINTER(c_void), ctypes.c_char_p]),
     "rgbd_peer_comm_connect": (c_int, [c_void, ctypes.c_char_p]),
     "rgbd_peer_comm_destroy": (c_int, [c_void]),
+    "rgbd_peer_comm_wait": (c_int, [c_void, c_void]),
     "rgbd_consistency_workspace_bytes": (c_size, [c_int, c_int, c_int, c_int]),
     "rgbd_consistency_fwd": (c_int, [c_void] * 6 + [c_int] * 4 + [ctypes.POINTER(LossOpts), c_void, c_void, c_void,
                                                                  c_void, c_size, c_void]),

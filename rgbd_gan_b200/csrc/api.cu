@@ -65,6 +65,10 @@ RGBD_API int rgbd_peer_comm_create(int rank, int world, void **comm_out, unsigne
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     memcpy(ipc_handle_out, &h, 64);
     pc->args.rank = rank; pc->args.world = world; pc->args.box[rank] = pc->mine;
+    e = cudaStreamCreateWithFlags(&pc->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pc->ev_main_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pc->ev_fin_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) { set_error("rgbd_peer_comm_create: %s", cudaGetErrorString(e)); return (int)e; }
     *comm_out = pc;
     return 0;
 }
@@ -97,8 +101,22 @@ RGBD_API int rgbd_peer_comm_destroy(void *comm)
     if (!pc) return 0;
     for (int r = 0; r < pc->args.world; ++r)
         if (r != pc->args.rank && pc->args.box[r]) cudaIpcCloseMemHandle(pc->args.box[r]);
+    if (pc->side) { cudaStreamSynchronize(pc->side); cudaStreamDestroy(pc->side); }
+    if (pc->ev_main_done) cudaEventDestroy(pc->ev_main_done);
+    if (pc->ev_fin_done) cudaEventDestroy(pc->ev_fin_done);
     if (pc->mine) cudaFree(pc->mine);
     delete pc;
+    return 0;
+}
+
+RGBD_API int rgbd_peer_comm_wait(void *comm, void *stream)
+{
+    using namespace rgbd;
+    rgbd_peer_comm *pc = (rgbd_peer_comm *)comm;
+    if (!pc) { set_error("rgbd_peer_comm_wait: null comm"); return RGBD_E_ARG; }
+    if (!pc->fin_pending) return 0;
+    const cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, pc->ev_fin_done, 0);
+    if (e != cudaSuccess) { set_error("rgbd_peer_comm_wait: %s", cudaGetErrorString(e)); return (int)e; }
     return 0;
 }
 

@@ -37,6 +37,11 @@ struct rgbd_peer_comm {               // host object behind the opaque handle of
     PeerArgs args;
     rgbd_mailbox *mine;
     bool connected;
+    // deferred-loss mode: the finalize + exchange kernel runs on `side`, forked after the main kernel
+    cudaStream_t side;
+    cudaEvent_t ev_main_done, ev_fin_done;
+    bool fin_pending;                 // ev_fin_done has been recorded and not yet waited on by the main stream
+    unsigned long long calls;         // parity selects one of two partial-sum buffers
 };
 
 struct Pose {          // one warp direction of one pair

@@ -43,6 +43,11 @@ class PeerComm:
     def handle(self):
         return self._h
 
+    def wait(self, stream=None):
+        """make `stream` (default: current) wait for the latest deferred loss exchange (defer_loss=True)"""
+        st = torch.cuda.current_stream() if stream is None else stream
+        _lib.check(_lib.load().rgbd_peer_comm_wait(self._h, ctypes.c_void_p(st.cuda_stream)), "rgbd_peer_comm_wait")
+
     def close(self):
         if self._h:
             torch.cuda.synchronize()

@@ -124,6 +124,8 @@ class _ConsistencyFn(torch.autograd.Function):
         owner.last_loss_parts = parts
         if owner.process_group is not None:
             loss = owner._allreduce_combine(parts)
+        elif owner.defer_loss:
+            loss = parts[4]                   # becomes valid after owner.peer_comm.wait(); do not touch it before
         else:
             loss = parts[4].clone()
         if new_zp is None:
@@ -167,12 +169,16 @@ class LossFuncRotate:
                          loss means are all-reduced (4 floats, NCCL), gradients need no communication.
       n_pairs_global  -- total number of pairs over all shards (default: local pairs x world size,
                          i.e. equal shards).
+      defer_loss      -- with peer_comm: the loss exchange is not joined into the current stream; the
+                         returned loss is valid after `peer_comm.wait()` (gradients are unaffected).  The
+                         exchange then overlaps the rest of the step, as a training loop that only logs
+                         the loss (updater.py:361, chainer.report) allows.
       peer_comm       -- rgbd_gan_b200.distributed.PeerComm: same sharding, but the 4 floats are
                          exchanged inside the loss kernel over NVLink peer memory (no NCCL launch).
     """
 
     def __init__(self, xp=None, K=None, norm="l1", lambda_geometric=3, *, grad_scale=None, return_new_zp=True,
-                 process_group=None, peer_comm=None, n_pairs_global=None):
+                 process_group=None, peer_comm=None, n_pairs_global=None, defer_loss=False):
         self.xp = xp
         self.size = None
         self.K = K
@@ -185,6 +191,7 @@ class LossFuncRotate:
         self.process_group = process_group
         self.peer_comm = peer_comm
         self.n_pairs_global = n_pairs_global
+        self.defer_loss = bool(defer_loss) and peer_comm is not None
         if peer_comm is not None and process_group is not None:
             raise ValueError("give either process_group (NCCL all-reduce) or peer_comm (fused), not both")
         self.last_loss_parts = None
@@ -231,7 +238,8 @@ class LossFuncRotate:
                         float("nan") if max_depth is None else float(max_depth),
                         float("nan") if min_depth is None else float(min_depth),
                         float(self.lambda_geometric),
-                        int(self.n_pairs_global) if self.n_pairs_global else int(B) * world, peer)
+                        int(self.n_pairs_global) if self.n_pairs_global else int(B) * world, peer,
+                        int(self.defer_loss), 0)
 
     def _allreduce_combine(self, parts):
         """sum the four per-shard means over the group, then combine as :141-144 (fp32)"""

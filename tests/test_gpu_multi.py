@@ -38,16 +38,20 @@ def _worker(rank, world, port, name, out_dir):
     x = torch.from_numpy(g["x"]).cuda()
     res = {}
     comm = PeerComm()
-    for mode in ("peer", "nccl", "peer_fused"):
+    for mode in ("peer", "nccl", "peer_fused", "peer_deferred"):
         kw = dict(peer_comm=comm) if mode.startswith("peer") else dict(process_group=dist.group.WORLD)
-        if mode == "peer_fused":
+        if mode in ("peer_fused", "peer_deferred"):
             kw["grad_scale"] = o["gy"]
+        if mode == "peer_deferred":
+            kw["defer_loss"] = True
         f = LossFuncRotate(None, norm=o["norm"], lambda_geometric=o["lam"], n_pairs_global=B, **kw)
         for rep in range(3):                      # several calls: epochs advance, mailbox slots are reused
             img = x[:B][lo:hi].clone().requires_grad_(True)
             img_rot = x[B:][lo:hi].clone().requires_grad_(True)
             loss, _ = f(img, g["cam"][:B][lo:hi], img_rot, g["cam"][B:][lo:hi], occlusion_aware=o["occ"])
             (loss * o["gy"]).backward()
+        if mode == "peer_deferred":
+            comm.wait()                           # only now may the loss be read
         res[mode + "_loss"] = loss.detach().cpu().numpy()
         res[mode + "_gi"] = img.grad.cpu().numpy()
         res[mode + "_gr"] = img_rot.grad.cpu().numpy()
@@ -65,7 +69,7 @@ def test_sharded_pairs_two_gpus(name, tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
     g = load_golden(name)
     outs = [np.load(tmp_path / ("rank%d.npz" % r)) for r in range(world)]
-    for mode in ("peer", "nccl", "peer_fused"):
+    for mode in ("peer", "nccl", "peer_fused", "peer_deferred"):
         for d in outs:
             assert abs(float(d[mode + "_loss"]) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
             lo, hi = int(d["lo"]), int(d["hi"])
