@@ -300,7 +300,9 @@ def run_ours(a):
             step_fused(pool[k % pool_n])             # every rank must make the same sequence of loss calls)
         torch.cuda.synchronize(dev)
 
-    use_graph = (not a.no_graph) and peer is None      # a deferred exchange cannot live inside a stream capture
+    # direct launches (PDL chain) are the default: measured 27.9 us/step vs 28.9 us/step for CUDA-graph replays
+    # of the same calls (profiles/r01_tuning.md); --graph switches to graph replays (not with a deferred exchange)
+    use_graph = a.graph and peer is None
     graphs_fused = capture(step_fused) if use_graph else None
     graphs_two = capture(step_two_pass) if use_graph else None
 
@@ -560,7 +562,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=32)
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--depth", default="rough", choices=["rough", "smooth"])
-    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="(default; kept for compatibility)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -120,6 +120,29 @@ def _full_parts(g, o, oracle_mod):
     return oracle_mod.consistency_fwd(g["x"][:B], g["x"][B:], M, c, Mi, -ci, norm=1, occlusion=o["occ"])
 
 
+@pytest.mark.parametrize("name", ["loss_cfg0_l1_occ", "loss_s64_l1_noocc", "loss_edge_wild", "loss_s32_l2_noocc", "loss_car_l1_occ"])
+@pytest.mark.parametrize("band", ["0", "1"])
+@pytest.mark.parametrize("band_tr", ["0", "8"])
+def test_band_and_staged_kernels_agree_with_reference(name, band, band_tr, monkeypatch):
+    """C=4 has two main kernels: the staged fast kernel (default) and the opt-in shared-memory band kernel
+    (no staging copy, RGBD_B200_BAND=1).  Both must reproduce the reference; a small band (TR=8) forces the
+    out-of-band global fallback of the gather to be exercised."""
+    monkeypatch.setenv("RGBD_B200_BAND", band)
+    monkeypatch.setenv("RGBD_B200_BAND_TR", band_tr)
+    g = load_golden(name)
+    o = case_options(g)
+    drv = _driver(g, o)
+    parts, gi, gr = drv.fwd_bwd(gy=o["gy"])
+    assert abs(parts[4] - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert_grad_close(gi, g["g_img"])
+    assert_grad_close(gr, g["g_img_rot"])
+    parts2, _, _ = drv.fwd(want_zp=False, want_masks=False)
+    np.testing.assert_allclose(parts2[:5], parts[:5], rtol=1e-6)
+    gi2, gr2 = drv.bwd(gy=o["gy"])
+    assert_grad_close(gi2, g["g_img"])
+    assert_grad_close(gr2, g["g_img_rot"])
+
+
 def test_growing_sizes_reuse():
     g = load_golden("loss_growing")
     from gpu_util import Consistency
