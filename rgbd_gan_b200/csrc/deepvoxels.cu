@@ -200,13 +200,17 @@ __device__ __forceinline__ void dv_elem_taps(const float vc[3], int G, int F, El
 }
 
 constexpr int kDvWarps = 8;
+constexpr int kDvTileStride = 36;        // floats per tile row: 16-byte aligned rows for the float4 accesses
 
-// one warp = 32 consecutive frustum elements; lane = feature while gathering, lane = element while storing
+// One warp = 32 consecutive frustum elements.  While gathering, a lane is (element slot eg = lane/8,
+// feature quad fq = lane%8): four kept elements are processed per iteration, each 8-lane group reading the
+// 128-byte feature line of one corner with 16-byte loads.  While storing, lane = element (coalesced along l).
 __global__ void __launch_bounds__(32 * kDvWarps)
 k_dv_project_fwd_cl(const rgbd_dv_params P, const float *__restrict__ cl, const float *__restrict__ cam2world,
                     int F, float *__restrict__ frustum)
 {
-    __shared__ float tile[kDvWarps][32][33];
+    __shared__ __align__(16) float tile[kDvWarps][32][kDvTileStride];
+    __shared__ unsigned char elist[kDvWarps][32];                      // lanes of the kept elements, in order
     const int n = P.W * P.H * P.D;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b = blockIdx.y;
@@ -218,36 +222,46 @@ k_dv_project_fwd_cl(const rgbd_dv_params P, const float *__restrict__ cl, const 
     const bool keep = (l < n) && dv_coords(P, T, l, vc);
     ElemTaps mine = {};
     if (keep) dv_elem_taps(vc, P.G, F, mine);
-    const unsigned kept = __ballot_sync(0xffffffffu, keep);
-    const size_t G3 = (size_t)P.G * P.G * P.G;
-    float (*tl)[33] = tile[wid];
     const unsigned FULL = 0xffffffffu;
+    const unsigned kept = __ballot_sync(FULL, keep);
+    const int nk = __popc(kept);
+    if (keep) elist[wid][__popc(kept & ((1u << lane) - 1u))] = (unsigned char)lane;
+    __syncwarp();
+    const int eg = lane >> 3, fq = lane & 7;
+    const size_t G3 = (size_t)P.G * P.G * P.G;
+    float (*tl)[kDvTileStride] = tile[wid];
     for (int f0 = 0; f0 < F; f0 += 32) {
-        const int f = f0 + lane;
         const float *__restrict__ src = cl + (size_t)b * G3 * F;
-        const int fl = f < F ? f : 0;
+        const int f = f0 + 4 * fq;
 #pragma unroll 4
         for (int e = 0; e < 32; ++e) tl[e][lane] = 0.0f;               // elements outside the grid stay 0
-        for (unsigned rem = kept; rem; rem &= rem - 1) {               // warp-uniform loop over kept elements
-            const int e = __ffs(rem) - 1;
+        __syncwarp();
+        for (int it = 0; it < nk; it += 4) {                           // warp-uniform trip count
+            const int idx = it + eg;
+            const bool active = idx < nk;
+            const int e = active ? (int)elist[wid][idx] : 0;           // lane that owns the idx-th kept element
             const float wx0 = __shfl_sync(FULL, mine.wx0, e), wx1 = __shfl_sync(FULL, mine.wx1, e);
             const float wy0 = __shfl_sync(FULL, mine.wy0, e), wy1 = __shfl_sync(FULL, mine.wy1, e);
             const float wz0 = __shfl_sync(FULL, mine.wz0, e), wz1 = __shfl_sync(FULL, mine.wz1, e);
-            float v[8];
+            int off[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __ldg(src + (__shfl_sync(FULL, mine.off[k], e) + fl));
-            // each term ((v*wx)*wy)*wz, summed left to right in the corner order of deepvoxel.py:416-423
-#define RGBD_TERM(K_, WX_, WY_, WZ_) __fmul_rn(__fmul_rn(__fmul_rn(v[K_], WX_), WY_), WZ_)
-            float acc = RGBD_TERM(0, wx0, wy0, wz0);
-            acc = __fadd_rn(acc, RGBD_TERM(1, wx1, wy0, wz0));
-            acc = __fadd_rn(acc, RGBD_TERM(2, wx0, wy1, wz0));
-            acc = __fadd_rn(acc, RGBD_TERM(3, wx0, wy0, wz1));
-            acc = __fadd_rn(acc, RGBD_TERM(4, wx1, wy0, wz1));
-            acc = __fadd_rn(acc, RGBD_TERM(5, wx0, wy1, wz1));
-            acc = __fadd_rn(acc, RGBD_TERM(6, wx1, wy1, wz0));
-            acc = __fadd_rn(acc, RGBD_TERM(7, wx1, wy1, wz1));
+            for (int k = 0; k < 8; ++k) off[k] = __shfl_sync(FULL, mine.off[k], e);
+            if (active && f < F) {
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = __ldg(reinterpret_cast<const float4 *>(src + (off[k] + f)));
+                // each term ((v*wx)*wy)*wz, summed left to right in the corner order of deepvoxel.py:416-423
+#define RGBD_TERM(K_, C_, WX_, WY_, WZ_) __fmul_rn(__fmul_rn(__fmul_rn(v[K_].C_, WX_), WY_), WZ_)
+#define RGBD_SUM(C_)                                                                                   \
+    __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(RGBD_TERM(0, C_, wx0, wy0, wz0), \
+        RGBD_TERM(1, C_, wx1, wy0, wz0)), RGBD_TERM(2, C_, wx0, wy1, wz0)), RGBD_TERM(3, C_, wx0, wy0, wz1)), \
+        RGBD_TERM(4, C_, wx1, wy0, wz1)), RGBD_TERM(5, C_, wx0, wy1, wz1)), RGBD_TERM(6, C_, wx1, wy1, wz0)), \
+        RGBD_TERM(7, C_, wx1, wy1, wz1))
+                const float4 acc = make_float4(RGBD_SUM(x), RGBD_SUM(y), RGBD_SUM(z), RGBD_SUM(w));
+#undef RGBD_SUM
 #undef RGBD_TERM
-            tl[e][lane] = acc;                                          // row = element, column = feature
+                *reinterpret_cast<float4 *>(&tl[e][4 * fq]) = acc;     // row = element, columns = features
+            }
         }
         __syncwarp();
         if (l < n) {
@@ -263,7 +277,8 @@ __global__ void __launch_bounds__(32 * kDvWarps)
 k_dv_project_bwd_cl(const rgbd_dv_params P, const float *__restrict__ g_frustum, const float *__restrict__ cam2world,
                     int F, float *__restrict__ gcl)
 {
-    __shared__ float tile[kDvWarps][32][33];
+    __shared__ __align__(16) float tile[kDvWarps][32][kDvTileStride];
+    __shared__ unsigned char elist[kDvWarps][32];
     const int n = P.W * P.H * P.D;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b = blockIdx.y;
@@ -275,17 +290,25 @@ k_dv_project_bwd_cl(const rgbd_dv_params P, const float *__restrict__ g_frustum,
     const bool keep = (l < n) && dv_coords(P, T, l, vc);
     ElemTaps mine = {};
     if (keep) dv_elem_taps(vc, P.G, F, mine);
-    const unsigned kept = __ballot_sync(0xffffffffu, keep);
+    const unsigned FULL = 0xffffffffu;
+    const unsigned kept = __ballot_sync(FULL, keep);
     if (kept == 0u) return;
+    const int nk = __popc(kept);
+    if (keep) elist[wid][__popc(kept & ((1u << lane) - 1u))] = (unsigned char)lane;
     // the lift only needs 1e-5: fold the three factors of every corner once per element (owner lane)
     float w[8];
     w[0] = (mine.wz0 * mine.wy0) * mine.wx0; w[1] = (mine.wz0 * mine.wy0) * mine.wx1;
     w[2] = (mine.wz0 * mine.wy1) * mine.wx0; w[3] = (mine.wz1 * mine.wy0) * mine.wx0;
     w[4] = (mine.wz1 * mine.wy0) * mine.wx1; w[5] = (mine.wz1 * mine.wy1) * mine.wx0;
     w[6] = (mine.wz0 * mine.wy1) * mine.wx1; w[7] = (mine.wz1 * mine.wy1) * mine.wx1;
+    const int eg = lane >> 3, fq = lane & 7;
+    // each 8-lane group walks a CONTIGUOUS quarter of the kept elements: neighbouring elements of an image row
+    // usually fall into the same voxel cell, so their contributions to a corner are summed in registers and
+    // leave as ONE 128-byte RED per run (the L2 atomic traffic, 8 lines per element, was the limiter)
+    const int q = (nk + 3) >> 2;
+    const int lo = eg * q, hi = min(nk, lo + q);
     const size_t G3 = (size_t)P.G * P.G * P.G;
-    float (*tl)[33] = tile[wid];
-    const unsigned FULL = 0xffffffffu;
+    float (*tl)[kDvTileStride] = tile[wid];
     for (int f0 = 0; f0 < F; f0 += 32) {
         const int fmax = min(32, F - f0);
         if (l < n) {
@@ -293,18 +316,31 @@ k_dv_project_bwd_cl(const rgbd_dv_params P, const float *__restrict__ g_frustum,
             for (int ff = 0; ff < fmax; ++ff) tl[lane][ff] = __ldg(go + (size_t)ff * n);   // coalesced along l
         }
         __syncwarp();
-        const int f = f0 + lane;
         float *__restrict__ dst = gcl + (size_t)b * G3 * F;
-        const int fl = f < F ? f : 0;
-        for (unsigned rem = kept; rem; rem &= rem - 1) {
-            const int e = __ffs(rem) - 1;
-            const float g = tl[e][lane];
+        const int f = f0 + 4 * fq;
+        const bool fok = f < F;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 8; ++k) {
+            int prev = -1;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int it = 0; it < q; ++it) {                           // warp-uniform trip count
+                const int idx = lo + it;
+                const bool active = idx < hi;
+                const int e = active ? (int)elist[wid][idx] : 0;
                 const int off = __shfl_sync(FULL, mine.off[k], e);
                 const float wk = __shfl_sync(FULL, w[k], e);
-                if (f < F) atomicAdd(dst + (off + fl), g * wk);             // one 128-byte line per corner
+                if (active && fok) {
+                    const float4 g = *reinterpret_cast<const float4 *>(&tl[e][4 * fq]);
+                    if (off != prev) {
+                        if (prev >= 0) atomicAdd(reinterpret_cast<float4 *>(dst + (prev + f)), acc);
+                        prev = off;
+                        acc = make_float4(g.x * wk, g.y * wk, g.z * wk, g.w * wk);
+                    } else {
+                        acc.x += g.x * wk; acc.y += g.y * wk; acc.z += g.z * wk; acc.w += g.w * wk;
+                    }
+                }
             }
+            if (prev >= 0) atomicAdd(reinterpret_cast<float4 *>(dst + (prev + f)), acc);
         }
         __syncwarp();
     }
@@ -521,7 +557,7 @@ RGBD_API int rgbd_dv_project_fwd(const rgbd_dv_params *p, const float *grid, con
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int n = p->W * p->H * p->D;
-    if (!workspace) {                                     // planar fallback: no staging memory available
+    if (!workspace || (F & 3)) {                          // planar fallback: no staging memory, or F not a multiple of 4
         dim3 grid_dim((n + kThreads - 1) / kThreads, B);
         k_dv_project_fwd<<<grid_dim, kThreads, 0, st>>>(*p, grid, cam2world, F, frustum);
         count_launch();
@@ -554,7 +590,7 @@ RGBD_API int rgbd_dv_project_bwd(const rgbd_dv_params *p, const float *g_frustum
     cudaStream_t st = (cudaStream_t)stream;
     const int n = p->W * p->H * p->D;
     const size_t G3 = (size_t)p->G * p->G * p->G;
-    if (!workspace) {
+    if (!workspace || (F & 3)) {
         cudaError_t e = cudaMemsetAsync(g_grid, 0, sizeof(float) * (size_t)B * F * G3, st);
         if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
         dim3 grid_dim((n + kThreads - 1) / kThreads, B);

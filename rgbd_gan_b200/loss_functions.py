@@ -140,8 +140,9 @@ class _ConsistencyFn(torch.autograd.Function):
         if g_loss is None:
             g_loss = torch.zeros((), dtype=torch.float32, device=img.device)
         g_loss = g_loss.to(torch.float32).contiguous()
-        if ctx.fused and g_new_zp is None:
+        if ctx.fused and g_new_zp is None and ctx.stash is not None:
             g_img, g_img_rot = ctx.stash
+            ctx.stash = None                  # the stash is handed out once; a second backward recomputes
             _lib.call("rgbd_consistency_rescale", _ptr(g_img), _ptr(g_img_rot), g_img.numel(), _ptr(g_loss),
                       ctypes.c_float(owner.grad_scale), _stream())
             return g_img, g_img_rot, None, None, None, None
