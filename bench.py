@@ -82,7 +82,7 @@ def run_reference(a):
         return
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     S = a.size
-    steps, warmup = max(1, min(a.steps, 8)), max(0, min(a.warmup, 2))
+    steps, warmup = max(1, min(a.steps, 600)), max(0, min(a.warmup, 5))     # one step = procs x 4 pairs, ~70 ms
     sample = 4
     value, s_per_step, procs = cpu_port_throughput(S, a.depth, steps, warmup, sample_pairs=sample)
     line = {
@@ -547,16 +547,16 @@ def cpu_baseline_leg(a):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     t0 = time.perf_counter()
     v1 = 4 * 6 / _cpu_worker((4, a.size, a.depth, 0, 6))                       # single process, 1 core
-    value, _, procs = cpu_port_throughput(a.size, a.depth, steps=20, warmup=1, sample_pairs=4)
+    value, _, procs = cpu_port_throughput(a.size, a.depth, steps=100, warmup=1, sample_pairs=4)
     return {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "single_core_value": v1,
-            "sample": "oracle/numpy_port.py fwd+bwd (NumPy port of the Chainer CPU path), %d processes x 4 pairs x 20 "
+            "sample": "oracle/numpy_port.py fwd+bwd (NumPy port of the Chainer CPU path), %d processes x 4 pairs x 100 "
                       "steps at %dx%d, occlusion on; wall %.1f s" % (procs, a.size, a.size, time.perf_counter() - t0)}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=32)

@@ -139,3 +139,38 @@ def test_projection_helper_like_generator(name):
     cam = g["cam"][0].copy()
     cam[:3, 3] += 100.0
     assert h.compute_proj_idcs(cam) is None
+
+
+def test_calc_real_pos_matches_reference_formula():
+    """LossFuncRotate.calc_real_pos (loss_functions.py:148-158): real_pos = (R K^-1)(z p) + t, concatenated
+    with the RGB planes; no caller in the reference, plain array-library math here."""
+    from rgbd_gan_b200.loss_functions import LossFuncRotate
+    g = load_golden("loss_s64_l1_noocc")
+    o = case_options(g)
+    B, S = o["B"], o["S"]
+    x = torch.from_numpy(g["x"]).to(DEV)
+    f = LossFuncRotate(None)
+    f.init_params(None, size=S)
+    out = f.calc_real_pos(x[:B], g["cam"][:B]).cpu().numpy()
+    R, t = g["cam"][:B, :3, :3], g["cam"][:B, :3, -1:]
+    z = g["x"][:B, -1:].reshape(B, 1, -1)
+    ref = np.matmul(np.matmul(R, f.inv_K), z * f.p) + t
+    assert out.shape == (B, 6, S * S)
+    np.testing.assert_array_equal(out[:, :3], g["x"][:B, :3].reshape(B, 3, -1))
+    np.testing.assert_allclose(out[:, 3:], ref, rtol=1e-5, atol=1e-5)
+
+
+def test_interpolate_trilinear_batch_and_errors():
+    from rgbd_gan_b200.projection import ProjectionHelper, interpolate_trilinear
+    g = load_golden("dv_g16_f3")
+    G, img, F, D = int(g["G"]), int(g["img"]), int(g["F"]), int(g["D"])
+    h = ProjectionHelper(g["intrinsic"], g["intrinsic"], [img, img], [img, img], 0., 1., [G] * 3,
+                         float(g["voxel_size"]), g["near_plane"], D, verbose=False)
+    lin, vc = h.compute_proj_idcs(g["cam"][0])
+    grid = torch.from_numpy(g["grid"]).to(DEV)            # batch of 2 grids through the same index list
+    out = interpolate_trilinear(grid, lin, vc, [img, img], D)
+    np.testing.assert_array_equal(out[0].cpu().numpy(), g["frustum_0"][0])
+    with pytest.raises(TypeError):
+        interpolate_trilinear(grid.cpu(), lin, vc, [img, img], D)
+    with pytest.raises(ValueError):
+        interpolate_trilinear(grid[:, :, :, :, :8].contiguous(), lin, vc, [img, img], D)
