@@ -109,12 +109,15 @@ class _ConsistencyFn(torch.autograd.Function):
         pp = _pose_ptrs(poses, B)
         need_grad = img.requires_grad or img_rot.requires_grad
         ctx.owner, ctx.opts, ctx.poses, ctx.shape = owner, opts, poses, (B, C, H, W)
-        ctx.fused = owner.grad_scale is not None and need_grad
+        # one pass for loss + gradients whenever a gradient will be asked for; the expected upstream gradient
+        # defaults to 1 and backward rescales on the device if a different one arrives
+        ctx.fused = need_grad and owner.fuse_backward
+        ctx.expected_gy = 1.0 if owner.grad_scale is None else owner.grad_scale
         ctx.set_materialize_grads(False)
         if ctx.fused:
             g_img, g_img_rot = torch.empty_like(img), torch.empty_like(img_rot)
             _lib.call("rgbd_consistency_fwd_bwd", _ptr(img), _ptr(img_rot), *pp, B, C, H, W, ctypes.byref(opts),
-                      ctypes.c_float(owner.grad_scale), _ptr(parts), _ptr(new_zp), _ptr(g_img), _ptr(g_img_rot),
+                      ctypes.c_float(ctx.expected_gy), _ptr(parts), _ptr(new_zp), _ptr(g_img), _ptr(g_img_rot),
                       _ptr(ws), ws.numel(), _stream())
             ctx.stash = (g_img, g_img_rot)
         else:
@@ -144,7 +147,7 @@ class _ConsistencyFn(torch.autograd.Function):
             g_img, g_img_rot = ctx.stash
             ctx.stash = None                  # the stash is handed out once; a second backward recomputes
             _lib.call("rgbd_consistency_rescale", _ptr(g_img), _ptr(g_img_rot), g_img.numel(), _ptr(g_loss),
-                      ctypes.c_float(owner.grad_scale), _stream())
+                      ctypes.c_float(ctx.expected_gy), _stream())
             return g_img, g_img_rot, None, None, None, None
         ws = owner._workspace(B, C, H, W, img.device)
         g_img, g_img_rot = torch.empty_like(img), torch.empty_like(img_rot)
@@ -159,11 +162,14 @@ class LossFuncRotate:
     """Mirror of the reference class (common/loss_functions.py:31-168).
 
     Extra keyword-only arguments (not in the reference):
-      grad_scale      -- if set, forward also produces both image gradients for this upstream
-                         gradient in the same pass (rgbd_consistency_fwd_bwd); backward then
-                         only checks the gradient that arrives (device side) and rescales if it
-                         differs.  In the reference's loop the upstream gradient of this loss is
-                         the constant lambda_rotate (updater.py:363-365).
+      fuse_backward   -- (default True) when an input requires grad, forward produces the loss AND both
+                         image gradients in one pass (rgbd_consistency_fwd_bwd); backward then only
+                         compares the upstream gradient that arrives with the expected one on the device
+                         and rescales the stashed gradients if it differs.  False: forward computes the
+                         loss only and backward recomputes (rgbd_consistency_fwd / _bwd).
+      grad_scale      -- the expected upstream gradient of the fused path (default 1).  In the
+                         reference's loop it is the constant lambda_rotate (updater.py:363-365); giving
+                         it here makes the rescale pass a no-op.
       return_new_zp   -- materialise the second return value (:146).  No reference caller uses
                          it (updater.py:340 drops it); False returns None in its place.
       process_group   -- torch.distributed group over which the PAIRS are sharded; the four
@@ -179,7 +185,7 @@ class LossFuncRotate:
     """
 
     def __init__(self, xp=None, K=None, norm="l1", lambda_geometric=3, *, grad_scale=None, return_new_zp=True,
-                 process_group=None, peer_comm=None, n_pairs_global=None, defer_loss=False):
+                 process_group=None, peer_comm=None, n_pairs_global=None, defer_loss=False, fuse_backward=True):
         self.xp = xp
         self.size = None
         self.K = K
@@ -188,6 +194,7 @@ class LossFuncRotate:
         self.inv_K = None
         self.p = None
         self.grad_scale = None if grad_scale is None else float(grad_scale)
+        self.fuse_backward = bool(fuse_backward)
         self.return_new_zp = return_new_zp
         self.process_group = process_group
         self.peer_comm = peer_comm

@@ -32,8 +32,9 @@ def _run(name, **ctor):
 
 
 @pytest.mark.parametrize("name", LOSS_CASES)
-def test_loss_func_rotate_like_updater(name):
-    g, o, f, loss, zp, gi, gr = _run(name)
+@pytest.mark.parametrize("fuse", [True, False])
+def test_loss_func_rotate_like_updater(name, fuse):
+    g, o, f, loss, zp, gi, gr = _run(name, fuse_backward=fuse)
     assert loss.dim() == 0
     assert abs(loss.item() - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
     np.testing.assert_array_equal(zp.detach().cpu().numpy(), g["new_zp_cat"])
