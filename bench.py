@@ -431,7 +431,7 @@ def run_ours(a):
     return line, dict(dev=dev, world=world, rank=rank, lib=lib, hbm_peak=hbm_peak)
 
 
-def sweep(a, ctx_, sizes=((128, 256), (256, 256)), graph_like=False):
+def sweep(a, ctx_, sizes=((128, 256), (256, 256)), graph_like=False, hinge=None):
     """cfg4 of BASELINE.json: batch 256 at 128^2 and 256^2 (single GPU): pairs/s and step-level roofline.
     Also used for the generator-like smooth-depth variant of the headline workload."""
     import torch
@@ -453,6 +453,8 @@ def sweep(a, ctx_, sizes=((128, 256), (256, 256)), graph_like=False):
         parts = torch.zeros(8, device=dev)
         ws = torch.empty(lib.rgbd_consistency_workspace_bytes(B, C, S, S), dtype=torch.uint8, device=dev)
         opts = _lib.LossOpts(_lib.NORM_L1, 1, float("nan"), float("nan"), LAMBDA_GEO, B, None)
+        if hinge is not None:
+            opts.hinge_depth_min, opts.hinge_lambda = hinge
         base = pv.data_ptr()
         pp = [ctypes.c_void_p(base + 4 * o) for o in (0, 9 * B, 12 * B, 21 * B)]
 
@@ -586,6 +588,8 @@ def main():
             a2 = argparse.Namespace(**vars(a))
             a2.depth = "smooth"
             line["smooth_depth"] = sweep(a2, ctx_, sizes=((a.size, a.pairs),), graph_like=False)[0]
+        # next row: the updaters' depth hinge (yml: depth_min 1.0, lambda_depth 10) fused in
+        line["with_depth_hinge"] = sweep(a, ctx_, sizes=((a.size, a.pairs),), hinge=(1.0, 10.0))[0]
         line["deepvoxels"] = deepvoxels_bench(ctx_)
     if not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg(a)

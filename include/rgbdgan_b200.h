@@ -80,6 +80,11 @@ typedef struct {
                              comm).  The exchange then overlaps the stage-out of this call and the
                              stage-in of the next one.  Not usable under CUDA-graph stream capture. */
     int reserved;
+    float hinge_depth_min; /* "next" row fused around the loss (updater.py:357-359, C == 4 only):        */
+    float hinge_lambda;    /* loss_rotate += mean(relu(depth_min - depth)^2) * lambda_depth over both      */
+                           /* images; NaN depth_min or lambda <= 0 = off.  loss_parts[5] = that term,       */
+                           /* loss_parts[6] = loss_parts[4] + loss_parts[5]; its gradient (times the         */
+                           /* upstream gradient) is added to the depth channel of g_img / g_img_rot.          */
 } rgbd_loss_opts;
 
 /* ---- LossFuncRotate.__call__ : common/loss_functions.py:63-146 (+ warp :171-175,
@@ -95,7 +100,8 @@ RGBD_API size_t rgbd_consistency_workspace_bytes(int B, int C, int H, int W);
 /* Forward only.  loss_parts (device, 8 floats): [0..3] = the four means of :141-144 restricted
  * to these B pairs, in the order {rgb, rgb_rot, depth, depth_rot}; [4] = the loss combined as
  * :141-144 does, (p0+p1) + (p2*lambda + p3*lambda), valid as is when the batch is not sharded
- * (sharded: all-reduce [0..3] and recombine); [5..7] = 0, reserved.
+ * (sharded: all-reduce [0..3] and recombine); [5] = depth-hinge term and [6] = [4] + [5] (see
+ * rgbd_loss_opts.hinge_*; [5] = 0 when off); [7] = 0, reserved.
  * new_zp  (nullable): (2B,HW,3), the second return value of __call__ (:146).
  * masks   (nullable): (2,2B,HW) uint8 debug planes: [0] = not_getting_out (:215-216),
  *                     [1] = not_occluded (:114-115; 1 when occlusion_aware == 0).          */

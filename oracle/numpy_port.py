@@ -261,6 +261,21 @@ class LossFuncRotateNP:
         return gs1 + go2, gs2 + go1
 
 
+def depth_hinge(x_fake, depth_min, lambda_depth, gy=None):
+    """updater.py:357-359: F.mean(F.relu(depth_min - x_fake[:, -1]) ** 2) * lambda_depth, and (gy given) its
+    gradient w.r.t. x_fake, node by node"""
+    d = x_fake[:, -1]
+    h = np.maximum(f32(depth_min) - d, 0, dtype=f32)
+    sq = h ** f32(2)
+    val = (sq.mean(dtype=f32) * f32(lambda_depth)).astype(f32)
+    if gy is None:
+        return val
+    g = np.zeros_like(x_fake)
+    g_mean = np.broadcast_to((f32(lambda_depth) * f32(gy)) * f32(1.0 / sq.size), sq.shape)
+    g[:, -1] = -((f32(2) * h * g_mean) * (h > 0))
+    return val, g
+
+
 # ---------------------------------------------------------------------- DeepVoxels projection
 class ProjectionHelperNP:
     """deepvoxel/projection.py:5-105 with fp32-pinned scalar semantics (Q6)."""

@@ -264,6 +264,35 @@ ORC_API int orc_consistency_bwd(const float *img, const float *img_rot, const fl
     return 0;
 }
 
+/* ---- "next" row: the depth hinge the updaters add right after the loss,
+ * loss_rotate += F.mean(F.relu(depth_min - x_fake[:, -1]) ** 2) * lambda_depth   (updater.py:357-359,
+ * updater_deepvoxels.py:198-199), over the depth channel of all 2B images.
+ * Returns the term in *hinge_out; when g_img / g_img_rot are given, ADDS its gradient for upstream gy
+ * to their depth channel (Chainer: MulConstant, Mean, PowVarConst, ReLU, SubFromConstant backward). */
+ORC_API int orc_depth_hinge(const float *img, const float *img_rot, int B, int C, int H, int W, float depth_min,
+                            float lambda_depth, long long n_pairs_global, float gy, double *hinge_out,
+                            float *g_img, float *g_img_rot)
+{
+    const size_t HW = (size_t)H * W, img_sz = (size_t)C * HW;
+    const double n = 2.0 * (double)n_pairs_global * (double)HW;
+    const float coef = (lambda_depth * gy) * (float)(1.0 / n);
+    double sum = 0.0;
+    for (int sel = 0; sel < 2; ++sel) {
+        const float *im = sel ? img_rot : img;
+        float *g = sel ? g_img_rot : g_img;
+        for (int b = 0; b < B; ++b)
+            for (size_t k = 0; k < HW; ++k) {
+                const size_t at = b * img_sz + (size_t)(C - 1) * HW + k;
+                float h = depth_min - im[at];
+                if (!(h > 0.0f)) h = 0.0f;
+                sum += (double)(h * h);
+                if (g) g[at] += -((2.0f * h) * coef);
+            }
+    }
+    *hinge_out = (double)lambda_depth * (sum / n);
+    return 0;
+}
+
 /* ---- standalone surface: warp / inv_warp / bilinear (common/loss_functions.py:171-228) ---- */
 
 /* new_zp[b,n,:] = M[b] (z[b,n] * p[:,n]) - cv[b]     (:171-175; inv_warp :178-182 with cv = -(K t)) */

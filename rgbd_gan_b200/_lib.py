@@ -25,7 +25,12 @@ class LossOpts(ctypes.Structure):
     """rgbd_loss_opts"""
     _fields_ = [("norm", c_int), ("occlusion_aware", c_int), ("max_depth", c_float), ("min_depth", c_float),
                 ("lambda_geometric", c_float), ("n_pairs_global", ctypes.c_longlong), ("peer_comm", c_void),
-                ("defer_loss", c_int), ("reserved", c_int)]
+                ("defer_loss", c_int), ("reserved", c_int), ("hinge_depth_min", c_float), ("hinge_lambda", c_float)]
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        if len(args) < 10 and "hinge_depth_min" not in kw:
+            self.hinge_depth_min = float("nan")          # depth hinge off unless asked for
 
 
 class DvParams(ctypes.Structure):

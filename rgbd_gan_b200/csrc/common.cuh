@@ -24,7 +24,7 @@ extern thread_local cudaEvent_t g_hook_start, g_hook_stop;   // rgbd_profile_hoo
 // ---- peer-memory mailbox for the fused loss all-reduce (one per rank, cudaMalloc + CUDA IPC)
 constexpr int kMaxPeers = 16;
 struct rgbd_mailbox {
-    float slot[2][kMaxPeers][4];      // [epoch parity][writer rank][4 loss means]
+    float slot[2][kMaxPeers][8];      // [epoch parity][writer rank][4 loss means, depth hinge, 3 spare]
     unsigned flag[2][kMaxPeers];      // epoch published by each writer
     unsigned epoch;                   // local: last completed epoch
     unsigned pad[31];

@@ -125,12 +125,13 @@ class _ConsistencyFn(torch.autograd.Function):
                       _ptr(parts), _ptr(new_zp), None, _ptr(ws), ws.numel(), _stream())
         ctx.save_for_backward(img, img_rot)
         owner.last_loss_parts = parts
+        k = 6 if opts.hinge_lambda > 0 and opts.hinge_depth_min == opts.hinge_depth_min else 4
         if owner.process_group is not None:
-            loss = owner._allreduce_combine(parts)
+            loss = owner._allreduce_combine(parts, k == 6)
         elif owner.defer_loss:
-            loss = parts[4]                   # becomes valid after owner.peer_comm.wait(); do not touch it before
+            loss = parts[k]                   # becomes valid after owner.peer_comm.wait(); do not touch it before
         else:
-            loss = parts[4].clone()
+            loss = parts[k].clone()
         if new_zp is None:
             return loss, None
         return loss, new_zp
@@ -234,7 +235,7 @@ class LossFuncRotate:
             self._ws = {key: ws}                       # keep one size only
         return ws
 
-    def _opts(self, occlusion_aware, max_depth, min_depth, B):
+    def _opts(self, occlusion_aware, max_depth, min_depth, B, depth_hinge=None):
         world = 1
         if self.process_group is not None:
             import torch.distributed as dist
@@ -247,18 +248,24 @@ class LossFuncRotate:
                         float("nan") if min_depth is None else float(min_depth),
                         float(self.lambda_geometric),
                         int(self.n_pairs_global) if self.n_pairs_global else int(B) * world, peer,
-                        int(self.defer_loss), 0)
+                        int(self.defer_loss), 0,
+                        float("nan") if depth_hinge is None else float(depth_hinge[0]),
+                        0.0 if depth_hinge is None else float(depth_hinge[1]))
 
-    def _allreduce_combine(self, parts):
-        """sum the four per-shard means over the group, then combine as :141-144 (fp32)"""
+    def _allreduce_combine(self, parts, with_hinge=False):
+        """sum the per-shard means over the group, then combine as :141-144 (fp32) [+ the depth hinge term]"""
         import torch.distributed as dist
-        p = parts[:4].clone()
+        p = parts[:6].clone()
         dist.all_reduce(p, op=dist.ReduceOp.SUM, group=self.process_group)
-        return combine_loss_parts(p, self.lambda_geometric)
+        loss = combine_loss_parts(p, self.lambda_geometric)
+        return loss + p[5] if with_hinge else loss
 
     # -- :63-146
     def __call__(self, img, theta, img_rot, theta_rot, occlusion_aware=False, debug=False, max_depth=None,
-                 min_depth=None):
+                 min_depth=None, depth_hinge=None):
+        """Reference signature (:63-64) plus `depth_hinge=(depth_min, lambda_depth)`: the term the updaters add
+        right after this call, loss_rotate += mean(relu(depth_min - x_fake[:, -1]) ** 2) * lambda_depth
+        (updater.py:357-359), evaluated inside the same kernels; the returned loss then includes it."""
         img = _dev_f32(img, "img")
         img_rot = _dev_f32(img_rot, "img_rot")
         if img.shape != img_rot.shape or img.dim() != 4:
@@ -272,7 +279,7 @@ class LossFuncRotate:
         if debug:
             return self._debug(img, img_rot, M, c, Mi, ci)
         poses = self._uploader.upload(M, c, Mi, ci, img.device)
-        opts = self._opts(occlusion_aware, max_depth, min_depth, B)
+        opts = self._opts(occlusion_aware, max_depth, min_depth, B, depth_hinge)
         return _ConsistencyFn.apply(img, img_rot, self, poses, opts, bool(self.return_new_zp))
 
     def _debug(self, img, img_rot, M, c, Mi, ci):

@@ -173,6 +173,11 @@ class Variable:
             return DivFromConstant(rhs).apply((self,))[0]
         return Div().apply((_preprocess_rhs(self, rhs), self))[0]
 
+    def __pow__(self, rhs):
+        if not numpy.isscalar(rhs):
+            raise TypeError("only Variable ** scalar is restated")
+        return PowVarConst(rhs).apply((self,))[0]
+
 
 def _preprocess_rhs(x, value):
     if isinstance(value, Variable):
@@ -388,6 +393,44 @@ class Div(FunctionNode):
         return tuple(out[i] for i in idx)
 
 
+class PowVarConst(FunctionNode):
+    """functions/math/basic_math.py: x ** c; backward c * x ** (c - 1) * gy"""
+
+    def __init__(self, value):
+        self.value = value
+
+    def forward(self, x):
+        self.x = x[0]
+        return _force_array(x[0] ** _preprocess_const(x[0], self.value)),
+
+    def backward(self, idx, gy):
+        v = _preprocess_const(self.x, self.value)
+        return _force_array(v * (self.x ** _preprocess_const(self.x, self.value - 1)) * _arr(gy[0])),
+
+
+class ReLU(FunctionNode):
+    """functions/activation/relu.py: maximum(x, 0); backward gy * (y > 0)"""
+
+    def forward(self, x):
+        self.y = _force_array(numpy.maximum(x[0], 0, dtype=x[0].dtype))
+        return self.y,
+
+    def backward(self, idx, gy):
+        return _force_array(_arr(gy[0]) * (self.y > 0)),
+
+
+class Mean(FunctionNode):
+    """functions/math/average.py (axis=None): x.mean(); backward gy / size broadcast"""
+
+    def forward(self, x):
+        self.shape, self.dtype = x[0].shape, x[0].dtype
+        return _force_array(x[0].mean(), x[0].dtype),
+
+    def backward(self, idx, gy):
+        n = int(numpy.prod(self.shape))
+        return numpy.broadcast_to(_arr(gy[0]) * self.dtype.type(1.0 / n), self.shape).astype(self.dtype),
+
+
 class DivFromConstant(FunctionNode):
     def __init__(self, value):
         self.value = value
@@ -550,6 +593,8 @@ functions.concat = lambda xs, axis=1: Concat(axis).apply(tuple(xs))[0]
 functions.scatter_add = lambda a, slices, b: ScatterAdd(slices).apply((a, b))[0]
 functions.mean_absolute_error = lambda x0, x1: MeanAbsoluteError().apply((x0, x1))[0]
 functions.mean_squared_error = lambda x0, x1: MeanSquaredError().apply((x0, x1))[0]
+functions.relu = lambda x: ReLU().apply((x,))[0]
+functions.mean = lambda x: Mean().apply((x,))[0]
 
 
 # --------------------------------------------------------- package registration

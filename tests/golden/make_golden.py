@@ -136,6 +136,28 @@ def consistency_case(lf, get_cam, Prior, name, seed, B, C, S, depth, pose, norm=
                                              out["not_out_rot"].mean()))
 
 
+def hinge_case(lf, get_cam, Prior, name, seed, B, S, depth, pose, depth_min, lambda_depth, gy=2.0):
+    """the generator-step expression around the loss, as updater.py:340-365 evaluates it:
+    loss_rotate = LossFuncRotate(...) ; loss_rotate += mean(relu(depth_min - x_fake[:, -1]) ** 2) * lambda_depth ;
+    loss_gen += loss_rotate * lambda_rotate ; loss_gen.backward()"""
+    F = chainer.functions
+    np.random.seed(seed)
+    thetas = Prior(Cfg(**pose)).sample(2 * B)
+    cam = get_cam(thetas)
+    x = make_images(B, 4, S, depth)
+    obj = lf.LossFuncRotate(xp, lambda_geometric=3)
+    img, img_rot = Variable(x[:B].copy()), Variable(x[B:].copy())
+    loss_rotate, _ = obj(img, cam[:B], img_rot, cam[B:], True)
+    x_fake = F.concat([img, img_rot], axis=0)
+    hinge = F.mean(F.relu(depth_min - x_fake[:, -1]) ** 2) * lambda_depth            # updater.py:357-359
+    total = loss_rotate + hinge
+    (total * gy).backward()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x=x, thetas=thetas, cam=cam, B=B, S=S, gy=gy,
+                        depth_min=depth_min, lambda_depth=lambda_depth, loss_rotate=loss_rotate.array,
+                        hinge=hinge.array, total=total.array, g_img=img.grad, g_img_rot=img_rot.grad)
+    print("%-22s loss_rotate=%.9g hinge=%.9g" % (name, float(loss_rotate.array), float(hinge.array)))
+
+
 def growing_case(lf, get_cam, Prior, name, seed):
     """Q9: one LossFuncRotate instance reused across sizes 32 -> 64 (K mutated in place)."""
     np.random.seed(seed)
@@ -221,6 +243,9 @@ def main():
       translate=(0.3, 0.2, 0.4))
     c("loss_edge_c2", 8, B=1, C=2, S=16, depth="rough", pose=FFHQ, occ=True, lam=3)
     growing_case(lf, get_cam, Prior, "loss_growing", 9)
+    # next row: the depth hinge the updaters add to the loss, yml values of the configs
+    hinge_case(lf, get_cam, Prior, "hinge_ffhq", 12, B=2, S=64, depth="rough", pose=FFHQ, depth_min=1.0, lambda_depth=10)
+    hinge_case(lf, get_cam, Prior, "hinge_car", 13, B=3, S=32, depth="smooth", pose=CAR, depth_min=0.6, lambda_depth=10)
     # DeepVoxels projection: scaled-down geometry with several features, and the
     # production geometry (deepvoxels_generator.py:229-253) with one feature
     dv_case(pj, dv, get_cam, Prior, "dv_g16_f3", 10, G=16, img=32, F=3, nsamp=2)

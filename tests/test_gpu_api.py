@@ -175,3 +175,19 @@ def test_interpolate_trilinear_batch_and_errors():
         interpolate_trilinear(grid.cpu(), lin, vc, [img, img], D)
     with pytest.raises(ValueError):
         interpolate_trilinear(grid[:, :, :, :, :8].contiguous(), lin, vc, [img, img], D)
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+def test_depth_hinge_through_python_mirror(fuse):
+    from rgbd_gan_b200.loss_functions import LossFuncRotate
+    g = load_golden("hinge_ffhq")
+    B, gy = int(g["B"]), float(g["gy"])
+    x = torch.from_numpy(g["x"]).to(DEV)
+    img, img_rot = x[:B].clone().requires_grad_(True), x[B:].clone().requires_grad_(True)
+    f = LossFuncRotate(None, lambda_geometric=3, fuse_backward=fuse)
+    loss, _ = f(img, g["cam"][:B], img_rot, g["cam"][B:], True,
+                depth_hinge=(float(g["depth_min"]), float(g["lambda_depth"])))      # updater.py:340-359 in one call
+    (loss * gy).backward()
+    assert abs(loss.item() - float(g["total"])) <= 1e-5 * abs(float(g["total"]))
+    assert_grad_close(img.grad.cpu().numpy(), g["g_img"])
+    assert_grad_close(img_rot.grad.cpu().numpy(), g["g_img_rot"])

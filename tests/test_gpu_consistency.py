@@ -47,7 +47,7 @@ def test_forward_against_reference_golden(name):
     assert abs(parts[4] - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
     lam = np.float32(o["lam"])
     assert parts[4] == np.float32((parts[0] + parts[1]) + (parts[2] * lam + parts[3] * lam))
-    assert not parts[5:].any()
+    assert parts[5] == 0 and parts[6] == parts[4] and parts[7] == 0        # depth hinge off
 
 
 @pytest.mark.parametrize("name", LOSS_CASES)
@@ -252,3 +252,34 @@ def test_argument_validation_on_device():
     args[0] = p(mis)
     rc = lib.rgbd_consistency_fwd(*args, p(parts), None, None, p(drv.ws), drv.ws.numel(), stream())
     assert rc == -2
+
+
+@pytest.mark.parametrize("name", ["hinge_ffhq", "hinge_car"])
+def test_depth_hinge_fused_next_row(name, oracle_mod):
+    """SURVEY 8(f) rank 2, fused into the staging kernels: loss_rotate += mean(relu(depth_min - depth)^2) * lambda
+    (updater.py:357-359); against the reference's golden total / gradients and the C oracle."""
+    from gpu_util import Consistency
+    from oracle import numpy_port as npp
+    g = load_golden(name)
+    B, S, gy = int(g["B"]), int(g["S"]), float(g["gy"])
+    dmin, lam = float(g["depth_min"]), float(g["lambda_depth"])
+    port = npp.LossFuncRotateNP(lambda_geometric=3)
+    port.init_params(S)
+    drv = Consistency(g["x"], g["cam"], B, port.K, port.inv_K, lam=3.0, occ=True)
+    drv.opts.hinge_depth_min, drv.opts.hinge_lambda = dmin, lam
+    parts, gi, gr = drv.fwd_bwd(gy=gy)
+    assert abs(parts[4] - float(g["loss_rotate"])) <= 1e-5 * abs(float(g["loss_rotate"]))
+    assert abs(parts[5] - float(g["hinge"])) <= 1e-5 * max(abs(float(g["hinge"])), 1e-12)
+    assert abs(parts[6] - float(g["total"])) <= 1e-5 * abs(float(g["total"]))
+    assert_grad_close(gi, g["g_img"])
+    assert_grad_close(gr, g["g_img_rot"])
+    parts2, _, _ = drv.fwd(want_zp=False, want_masks=False)
+    np.testing.assert_allclose(parts2[:7], parts[:7], rtol=1e-6, atol=1e-12)
+    gi2, gr2 = drv.bwd(gy=1.0, gy_dev=gy)
+    assert_grad_close(gi2, g["g_img"])
+    assert_grad_close(gr2, g["g_img_rot"])
+    # sharded denominators + several chunks
+    drv.opts.n_pairs_global = 2 * B
+    parts3, gi3, _ = drv.fwd_bwd(gy=gy)
+    np.testing.assert_allclose(parts3[5] * 2, parts[5], rtol=1e-6, atol=1e-12)
+    assert_grad_close(gi3 * 2, g["g_img"])

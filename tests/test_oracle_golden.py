@@ -169,3 +169,29 @@ def test_dv_empty_frustum(oracle_mod):
     assert helper.compute_proj_idcs(cam) is None
     fr = oracle_mod.dv_project_fwd(P, g["grid"][:1], cam[None])
     assert not fr.any()
+
+
+@pytest.mark.parametrize("name", ["hinge_ffhq", "hinge_car"])
+def test_depth_hinge_next_row(name, oracle_mod):
+    """loss_rotate += mean(relu(depth_min - depth)^2) * lambda_depth (updater.py:357-359)"""
+    g = load_golden(name)
+    B, S, gy = int(g["B"]), int(g["S"]), float(g["gy"])
+    dmin, lam = float(g["depth_min"]), float(g["lambda_depth"])
+    x, cam = g["x"], g["cam"]
+    port = npp.LossFuncRotateNP(lambda_geometric=3)
+    port.init_params(S)
+    M, c, Mi, ci = port.pose_algebra(cam[:B], cam[B:])
+    parts = oracle_mod.consistency_fwd(x[:B], x[B:], M, c, Mi, -ci, norm=1, occlusion=True)
+    gi, gr = oracle_mod.consistency_bwd(x[:B], x[B:], M, c, Mi, -ci, norm=1, occlusion=True, lambda_geometric=3, gy=gy)
+    hinge = oracle_mod.depth_hinge(x[:B], x[B:], dmin, lam, gy=gy, g_img=gi, g_img_rot=gr)
+    assert abs(hinge - float(g["hinge"])) <= 1e-6 * max(abs(float(g["hinge"])), 1e-12)
+    total = np.float32(oracle_mod.combine_loss(parts, 3)) + np.float32(hinge)
+    assert abs(float(total) - float(g["total"])) <= 1e-5 * abs(float(g["total"]))
+    assert_grad_close(gi, g["g_img"])
+    assert_grad_close(gr, g["g_img_rot"])
+    val, gx = npp.depth_hinge(x, dmin, lam, gy=gy)
+    assert abs(float(val) - float(g["hinge"])) <= 1e-6 * max(abs(float(g["hinge"])), 1e-12)
+    loss, _ = port.forward(x[:B], cam[:B], x[B:], cam[B:], occlusion_aware=True)
+    gi2, gr2 = port.backward(gy)
+    assert_grad_close(gi2 + gx[:B], g["g_img"])
+    assert_grad_close(gr2 + gx[B:], g["g_img_rot"])
