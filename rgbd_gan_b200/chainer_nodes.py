@@ -5,7 +5,7 @@ GPU tests exercise; only the array container (cupy.ndarray: `arr.data.ptr`, `cup
 stream().ptr`) and the autograd hook (chainer.FunctionNode) differ.
 
 Neither package can be installed in the build image, so this module is import-guarded and is NOT
-covered by the -m gpu tests; tests/test_host_logic.py checks its node logic against the Chainer-v7
+covered by the -m gpu tests; tests/test_chainer_nodes.py checks its node logic against the Chainer-v7
 shim with a recording fake of the library (argument order, shapes, retained state).
 
 Drop-in use in the reference:
@@ -81,7 +81,8 @@ class ConsistencyLoss(FunctionNode):
                           ctypes.byref(self.opts), _ptr(parts), _ptr(new_zp), None, _ptr(self.ws), self.ws.size,
                           _stream(xp))
         self.loss_parts = parts
-        return parts[4].reshape(()), new_zp          # parts[4] = (p0+p1) + (p2*l + p3*l), :141-144
+        # parts[4] = (p0+p1) + (p2*l + p3*l), :141-144; parts[6] adds the fused depth hinge (== parts[4] when off)
+        return parts[6].reshape(()), new_zp
 
     def backward(self, target_input_indexes, grad_outputs):
         xp = self.xp
@@ -138,7 +139,8 @@ class LossFuncRotate:
                             dtype="float32").reshape(3, -1)
 
     def __call__(self, img, theta, img_rot, theta_rot, occlusion_aware=False, debug=False, max_depth=None,
-                 min_depth=None):
+                 min_depth=None, depth_hinge=None):
+        """reference signature plus depth_hinge=(depth_min, lambda_depth): updater.py:357-359 fused in"""
         if debug:
             raise NotImplementedError("debug=True: use rgbd_gan_b200.loss_functions (warp/bilinear kernels)")
         xp = self.xp
@@ -154,7 +156,9 @@ class LossFuncRotate:
             self._ws = xp.empty(nbytes, dtype="uint8")
         opts = LossOpts(_lib.NORM_L1 if self.norm == "l1" else _lib.NORM_L2, int(bool(occlusion_aware)),
                         float("nan") if max_depth is None else float(max_depth),
-                        float("nan") if min_depth is None else float(min_depth), float(self.lambda_geometric), B, None)
+                        float("nan") if min_depth is None else float(min_depth), float(self.lambda_geometric), B, None,
+                        0, 0, float("nan") if depth_hinge is None else float(depth_hinge[0]),
+                        0.0 if depth_hinge is None else float(depth_hinge[1]))
         node = ConsistencyLoss(M, c, Mi, ci, opts, self._ws, self.grad_scale, xp=xp, lib=self._lib)
         loss, new_zp = node.apply((img, img_rot))
         return loss, new_zp

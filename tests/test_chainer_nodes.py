@@ -92,6 +92,10 @@ class OracleBackedLib:
         arrs = (_view(img, sh), _view(img_rot, sh), _view(M, (B, 9)), _view(c, (B, 3)), _view(Mi, (B, 9)), _view(ci, (B, 3)))
         return arrs, (B, C, H, W), o, kw
 
+    @staticmethod
+    def _hinge(o):
+        return (o.hinge_depth_min == o.hinge_depth_min) and o.hinge_lambda > 0
+
     def _fwd(self, arrs, dims, o, kw, parts, new_zp):
         B, C, H, W = dims
         p, d = self.oracle.consistency_fwd(*arrs, debug=True, **kw)
@@ -99,6 +103,10 @@ class OracleBackedLib:
         out[:4] = p
         out[4] = self.oracle.combine_loss(p, o.lambda_geometric)
         out[5:] = 0
+        if self._hinge(o):
+            out[5] = self.oracle.depth_hinge(arrs[0], arrs[1], o.hinge_depth_min, o.hinge_lambda,
+                                             n_pairs_global=kw["n_pairs_global"])
+        out[6] = out[4] + out[5]
         z = _view(new_zp, (2 * B, H * W, 3))
         if z is not None:
             z[...] = d["new_zp"]
@@ -115,6 +123,9 @@ class OracleBackedLib:
             gy = a[11].value
             self._fwd(arrs, dims, o, kw, a[12], a[13])
             gi, gr = self.oracle.consistency_bwd(*arrs, lambda_geometric=o.lambda_geometric, gy=gy, **kw)
+            if self._hinge(o):
+                self.oracle.depth_hinge(arrs[0], arrs[1], o.hinge_depth_min, o.hinge_lambda,
+                                        n_pairs_global=kw["n_pairs_global"], gy=gy, g_img=gi, g_img_rot=gr)
             _view(a[14], dims)[...] = gi
             _view(a[15], dims)[...] = gr
         elif name == "rgbd_consistency_bwd":
@@ -124,6 +135,9 @@ class OracleBackedLib:
             gy = a[11].value * (float(_view(a[12], (1,))[0]) if a[12].value else 1.0)
             gz = _view(a[13], (2 * B, H * W, 3))
             gi, gr = self.oracle.consistency_bwd(*arrs, lambda_geometric=o.lambda_geometric, gy=gy, g_new_zp=gz, **kw)
+            if self._hinge(o):
+                self.oracle.depth_hinge(arrs[0], arrs[1], o.hinge_depth_min, o.hinge_lambda,
+                                        n_pairs_global=kw["n_pairs_global"], gy=gy, g_img=gi, g_img_rot=gr)
             _view(a[14], dims)[...] = gi
             _view(a[15], dims)[...] = gr
         elif name == "rgbd_consistency_rescale":
@@ -173,3 +187,19 @@ def test_chainer_node_reproduces_reference(nodes, oracle_mod, name, grad_scale):
     expect = ["rgbd_consistency_fwd", "rgbd_consistency_bwd"] if grad_scale is None else \
              ["rgbd_consistency_fwd_bwd", "rgbd_consistency_rescale"]
     assert lib.calls == expect
+
+
+@pytest.mark.parametrize("grad_scale", [None, 2.0])
+def test_chainer_node_with_fused_depth_hinge(nodes, oracle_mod, grad_scale):
+    g = load_golden("hinge_ffhq")
+    B = int(g["B"])
+    lib = OracleBackedLib(oracle_mod)
+    f = nodes.LossFuncRotate(FakeXP(), lambda_geometric=3, grad_scale=grad_scale, lib=lib)
+    V = chainer_shim.Variable
+    img, img_rot = V(_wrap(g["x"][:B])), V(_wrap(g["x"][B:]))
+    loss, _ = f(img, g["cam"][:B], img_rot, g["cam"][B:], True,
+                depth_hinge=(float(g["depth_min"]), float(g["lambda_depth"])))
+    (loss * float(g["gy"])).backward()
+    assert abs(float(loss.array) - float(g["total"])) <= 1e-5 * abs(float(g["total"]))
+    assert_grad_close(np.asarray(img.grad), g["g_img"])
+    assert_grad_close(np.asarray(img_rot.grad), g["g_img_rot"])
