@@ -97,6 +97,13 @@ typedef struct {
 
 RGBD_API size_t rgbd_consistency_workspace_bytes(int B, int C, int H, int W);
 
+/* Health check of the single-launch pipeline kernel (C == 4 path): the first bytes of the workspace
+ * are its control block (ticket and per-pair dependency counters; all-zero between calls, initialised by the
+ * kernel itself on first use and restored by its last block).  Every dependency wait is bounded (2 s); a wait
+ * that expires -- only possible if the caller overwrites the head of the workspace while a call is in flight --
+ * raises a sticky flag instead of hanging the GPU.  Synchronises `stream`; *status_host = 0 ok, 1 timed out. */
+RGBD_API int rgbd_consistency_status(const void *workspace, void *stream, int *status_host);
+
 /* Forward only.  loss_parts (device, 8 floats): [0..3] = the four means of :141-144 restricted
  * to these B pairs, in the order {rgb, rgb_rot, depth, depth_rot}; [4] = the loss combined as
  * :141-144 does, (p0+p1) + (p2*lambda + p3*lambda), valid as is when the batch is not sharded
