@@ -143,6 +143,49 @@ def test_band_and_staged_kernels_agree_with_reference(name, band, band_tr, monke
     assert_grad_close(gr2, g["g_img_rot"])
 
 
+@pytest.mark.parametrize("name", ["loss_cfg0_l1_occ", "loss_s32_l2_noocc", "hinge_ffhq"])
+@pytest.mark.parametrize("lags", [("2", "3"), ("1", "1"), ("40", "40")])
+def test_pipeline_kernel_agrees_with_reference(name, lags, monkeypatch):
+    """Opt-in single-launch pipeline kernel (RGBD_B200_MEGA=1): stage-in, main and stage-out tickets of one
+    persistent launch ordered by per-pair dependency counters in the head of the workspace.  Same results as the
+    three-kernel chain for any lag (1 = dependency waits are exercised, 40 = fully sequential phases), the
+    control block is back in its rest state afterwards (repeated calls on one workspace), no wait timed out."""
+    import ctypes
+    from gpu_util import Consistency
+    from oracle import numpy_port as npp
+    from rgbd_gan_b200 import _lib
+    monkeypatch.setenv("RGBD_B200_MEGA", "1")
+    monkeypatch.setenv("RGBD_B200_MEGA_LAG_MAIN", lags[0])
+    monkeypatch.setenv("RGBD_B200_MEGA_LAG_SO", lags[1])
+    g = load_golden(name)
+    hinge = name.startswith("hinge")
+    if hinge:
+        port = npp.LossFuncRotateNP(lambda_geometric=3)
+        port.init_params(int(g["S"]))
+        drv = Consistency(g["x"], g["cam"], int(g["B"]), port.K, port.inv_K, lam=3.0, occ=True)
+        drv.opts.hinge_depth_min, drv.opts.hinge_lambda = float(g["depth_min"]), float(g["lambda_depth"])
+        gy, want, slot = float(g["gy"]), float(g["total"]), 6
+    else:
+        o = case_options(g)
+        drv = _driver(g, o)
+        gy, want, slot = o["gy"], float(g["loss"]), 4
+    for _ in range(2):
+        parts, gi, gr = drv.fwd_bwd(gy=gy)
+        assert abs(parts[slot] - want) <= 1e-5 * abs(want)
+        assert_grad_close(gi, g["g_img"])
+        assert_grad_close(gr, g["g_img_rot"])
+    parts2, zp, _ = drv.fwd()
+    if not hinge:
+        np.testing.assert_array_equal(zp, g["new_zp_cat"])
+    np.testing.assert_allclose(parts2[:7], parts[:7], rtol=1e-6, atol=1e-12)
+    gi2, gr2 = drv.bwd(gy=1.0, gy_dev=gy)
+    assert_grad_close(gi2, g["g_img"])
+    assert_grad_close(gr2, g["g_img_rot"])
+    status = ctypes.c_int(-1)
+    _lib.call("rgbd_consistency_status", ctypes.c_void_p(drv.ws.data_ptr()), None, ctypes.byref(status))
+    assert status.value == 0
+
+
 def test_growing_sizes_reuse():
     g = load_golden("loss_growing")
     from gpu_util import Consistency
