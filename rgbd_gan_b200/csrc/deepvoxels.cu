@@ -2,6 +2,8 @@
 //   ProjectionHelper.compute_proj_idcs  (deepvoxel/projection.py:48-105)
 //   interpolate_trilinear + its autograd (deepvoxel/deepvoxel.py:388-428)
 // Per-element recipe: SURVEY.md Appendix A2 (fp32-pinned scalar semantics, quirks Q5-Q8, Q10).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rgbd {
@@ -205,6 +207,11 @@ constexpr int kDvTileStride = 36;        // floats per tile row: 16-byte aligned
 // One warp = 32 consecutive frustum elements.  While gathering, a lane is (element slot eg = lane/8,
 // feature quad fq = lane%8): four kept elements are processed per iteration, each 8-lane group reading the
 // 128-byte feature line of one corner with 16-byte loads.  While storing, lane = element (coalesced along l).
+// EXACT: every term is ((v*wx)*wy)*wz summed left to right, as deepvoxel.py:416-423 evaluates it (bit-equal to the
+// reference's fp32 elementwise chain; 31 FP instructions per output).  !EXACT: the three factors of a corner are
+// folded once per element and a feature costs 8 FMAs -- same indices and masks, values within ~1e-7 relative
+// (the parity bar for floating-point outputs is 1e-5); this is the default, RGBD_B200_DV_EXACT=1 selects EXACT.
+template <bool EXACT>
 __global__ void __launch_bounds__(32 * kDvWarps)
 k_dv_project_fwd_cl(const rgbd_dv_params P, const float *__restrict__ cl, const float *__restrict__ cam2world,
                     int F, float *__restrict__ frustum)
@@ -230,6 +237,11 @@ k_dv_project_fwd_cl(const rgbd_dv_params P, const float *__restrict__ cl, const 
     const int eg = lane >> 3, fq = lane & 7;
     const size_t G3 = (size_t)P.G * P.G * P.G;
     float (*tl)[kDvTileStride] = tile[wid];
+    float wf[8];                                                       // !EXACT: folded corner weights of MY element
+    wf[0] = (mine.wx0 * mine.wy0) * mine.wz0; wf[1] = (mine.wx1 * mine.wy0) * mine.wz0;
+    wf[2] = (mine.wx0 * mine.wy1) * mine.wz0; wf[3] = (mine.wx0 * mine.wy0) * mine.wz1;
+    wf[4] = (mine.wx1 * mine.wy0) * mine.wz1; wf[5] = (mine.wx0 * mine.wy1) * mine.wz1;
+    wf[6] = (mine.wx1 * mine.wy1) * mine.wz0; wf[7] = (mine.wx1 * mine.wy1) * mine.wz1;
     for (int f0 = 0; f0 < F; f0 += 32) {
         const float *__restrict__ src = cl + (size_t)b * G3 * F;
         const int f = f0 + 4 * fq;
@@ -240,12 +252,28 @@ k_dv_project_fwd_cl(const rgbd_dv_params P, const float *__restrict__ cl, const 
             const int idx = it + eg;
             const bool active = idx < nk;
             const int e = active ? (int)elist[wid][idx] : 0;           // lane that owns the idx-th kept element
-            const float wx0 = __shfl_sync(FULL, mine.wx0, e), wx1 = __shfl_sync(FULL, mine.wx1, e);
-            const float wy0 = __shfl_sync(FULL, mine.wy0, e), wy1 = __shfl_sync(FULL, mine.wy1, e);
-            const float wz0 = __shfl_sync(FULL, mine.wz0, e), wz1 = __shfl_sync(FULL, mine.wz1, e);
             int off[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) off[k] = __shfl_sync(FULL, mine.off[k], e);
+            if (!EXACT) {
+                float w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w[k] = __shfl_sync(FULL, wf[k], e);
+                if (active && f < F) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(src + (off[k] + f)));
+                        acc.x = fmaf(v.x, w[k], acc.x); acc.y = fmaf(v.y, w[k], acc.y);
+                        acc.z = fmaf(v.z, w[k], acc.z); acc.w = fmaf(v.w, w[k], acc.w);
+                    }
+                    *reinterpret_cast<float4 *>(&tl[e][4 * fq]) = acc;
+                }
+                continue;
+            }
+            const float wx0 = __shfl_sync(FULL, mine.wx0, e), wx1 = __shfl_sync(FULL, mine.wx1, e);
+            const float wy0 = __shfl_sync(FULL, mine.wy0, e), wy1 = __shfl_sync(FULL, mine.wy1, e);
+            const float wz0 = __shfl_sync(FULL, mine.wz0, e), wz1 = __shfl_sync(FULL, mine.wz1, e);
             if (active && f < F) {
                 float4 v[8];
 #pragma unroll
@@ -570,11 +598,14 @@ RGBD_API int rgbd_dv_project_fwd(const rgbd_dv_params *p, const float *grid, con
     const int G3 = p->G * p->G * p->G;
     const int Bs = (int)dv_chunk_samples(p, B, F);
     float *cl = (float *)workspace;
+    const char *ex = getenv("RGBD_B200_DV_EXACT");
+    const bool exact = ex && ex[0] == '1';
     for (int b0 = 0; b0 < B; b0 += Bs) {
         const int nb = (B - b0 < Bs) ? (B - b0) : Bs;
         k_dv_to_cl<<<dim3((G3 + 31) / 32, (F + 31) / 32, nb), dim3(32, 8), 0, st>>>(grid + (size_t)b0 * F * G3, cl, F, G3);
-        k_dv_project_fwd_cl<<<dim3((n + 32 * kDvWarps - 1) / (32 * kDvWarps), nb), 32 * kDvWarps, 0, st>>>(
-            *p, cl, cam2world + 16 * (size_t)b0, F, frustum + (size_t)b0 * F * n);
+        const dim3 gd((n + 32 * kDvWarps - 1) / (32 * kDvWarps), nb);
+        if (exact) k_dv_project_fwd_cl<true><<<gd, 32 * kDvWarps, 0, st>>>(*p, cl, cam2world + 16 * (size_t)b0, F, frustum + (size_t)b0 * F * n);
+        else k_dv_project_fwd_cl<false><<<gd, 32 * kDvWarps, 0, st>>>(*p, cl, cam2world + 16 * (size_t)b0, F, frustum + (size_t)b0 * F * n);
         count_launch(2);
     }
     return check_launch("rgbd_dv_project_fwd");

@@ -66,3 +66,17 @@ def oracle_mod():
     import oracle
     oracle.build()
     return oracle
+
+
+def assert_frustum_close(got, ref, exact):
+    """fused DeepVoxels projection: `exact` (RGBD_B200_DV_EXACT=1) is bit-equal to the reference's fp32 chain
+    ((v*wx)*wy)*wz; the default folds the corner weights once per element (8 FMAs per feature): identical
+    zero pattern (the in-grid mask is computed the same way), values within 1e-5 of the tensor's max-norm."""
+    import numpy as np
+    if exact:
+        np.testing.assert_array_equal(got, ref)
+        return
+    assert got.shape == ref.shape
+    assert np.array_equal(got == 0, ref == 0) or np.abs(got[(got == 0) != (ref == 0)]).max() < 1e-30
+    scale = float(np.abs(ref).max())
+    assert float(np.abs(got - ref).max()) <= 1e-5 * scale, float(np.abs(got - ref).max()) / scale
