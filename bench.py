@@ -544,6 +544,75 @@ def deepvoxels_bench(ctx_):
     return out
 
 
+def render_bench(ctx_):
+    """next row: fused projection + accumulative render tail (rgbd_dv_render_fwd/_bwd), which
+    replaces project + occlusion MLP + cumsum/clip/diff + collapse + depth map without materialising the (B,F,D,H,W)
+    view volume.  Algorithmic bytes per sample fwd+bwd = 2*(F*G^3 + (F+2)*H*W)*4."""
+    import torch
+    from rgbd_gan_b200 import _lib, poses
+    dev, lib = ctx_["dev"], ctx_["lib"]
+    out = []
+    for G, B in ((32, 16), (64, 16)):
+        F, img, nf = 32, 64, 4
+        D = int(np.ceil(np.sqrt(3) * G))
+        vs = (1. / G) * 1.1 * 0.5
+        P = _lib.DvParams(img, img, D, G, 128., 128., 32., 32., float(np.float32(vs)), float(np.float32(np.sqrt(3) / 4)))
+        R = _lib.DvRenderParams(nf, D, 4.0, float(np.float32(np.sqrt(2) * np.sqrt(1.0 / (F + 1)))),
+                                float(np.float32(np.sqrt(2) * np.sqrt(1.0 / nf))))
+        np.random.seed(3)
+        thetas = poses.CameraParamPrior.from_ranges(poses.CAR_RANGES, True).sample(2 * B)[:B]
+        cam = torch.from_numpy(poses.get_camera_matries(thetas).reshape(B, 16)).to(dev)
+        rng = np.random.default_rng(3)
+        W1 = torch.from_numpy(rng.normal(size=(nf, F + 1)).astype(np.float32)).to(dev)
+        b1 = torch.from_numpy(rng.normal(scale=0.3, size=(nf,)).astype(np.float32)).to(dev)
+        W2 = torch.from_numpy(rng.normal(size=(nf,)).astype(np.float32)).to(dev)
+        b2 = torch.tensor([-0.5], device=dev)
+        n_sets = 4 if G == 32 else 2
+        grids = [torch.randn((B, F, G, G, G), device=dev) for _ in range(n_sets)]
+        ggs = [torch.empty((B, F, G ** 3), device=dev) for _ in range(n_sets)]
+        novel, depth, fg = torch.empty((B, F, img * img), device=dev), torch.empty((B, img * img), device=dev), torch.empty((B, img * img), device=dev)
+        g_novel, g_depth = torch.randn_like(novel), torch.randn_like(depth)
+        gW1, gb1, gW2, gb2 = torch.empty_like(W1), torch.empty_like(b1), torch.empty_like(W2), torch.empty_like(b2)
+        ws = torch.empty(lib.rgbd_dv_render_workspace_bytes(ctypes.byref(P), B, F), dtype=torch.uint8, device=dev)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        pw = [ctypes.c_void_p(t.data_ptr()) for t in (W1, b1, W2, b2)]
+
+        def fwd(k):
+            _lib.call("rgbd_dv_render_fwd", ctypes.byref(P), ctypes.byref(R), ctypes.c_void_p(grids[k % n_sets].data_ptr()),
+                      ctypes.c_void_p(cam.data_ptr()), *pw, B, F, ctypes.c_void_p(novel.data_ptr()),
+                      ctypes.c_void_p(depth.data_ptr()), ctypes.c_void_p(fg.data_ptr()), ctypes.c_void_p(ws.data_ptr()),
+                      ws.numel(), st)
+
+        def bwd(k):
+            _lib.call("rgbd_dv_render_bwd", ctypes.byref(P), ctypes.byref(R), ctypes.c_void_p(grids[k % n_sets].data_ptr()),
+                      ctypes.c_void_p(cam.data_ptr()), *pw, B, F, ctypes.c_void_p(g_novel.data_ptr()),
+                      ctypes.c_void_p(g_depth.data_ptr()), None, ctypes.c_void_p(ggs[k % n_sets].data_ptr()),
+                      *[ctypes.c_void_p(t.data_ptr()) for t in (gW1, gb1, gW2, gb2)], ctypes.c_void_p(ws.data_ptr()),
+                      ws.numel(), st)
+
+        def timeit(fn, reps=10):
+            for k in range(3):
+                fn(k)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(reps):
+                fn(k)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / reps
+
+        ms_f, ms_b = timeit(fwd), timeit(bwd)
+        alg = 2 * (F * G ** 3 + (F + 2) * img * img) * 4 * B
+        gbs = alg / ((ms_f + ms_b) * 1e-3) / 1e9
+        out.append({"G": G, "F": F, "frustum": [D, img, img], "batch": B, "fwd_ms": ms_f, "bwd_ms": ms_b,
+                    "samples_per_s": B / ((ms_f + ms_b) * 1e-3), "algorithmic_GBps": gbs,
+                    "frac_of_hbm_peak": gbs / ctx_["hbm_peak"], "saturated_rays": float((fg > 0.999999).float().mean().item())})
+        del grids, ggs
+        torch.cuda.empty_cache()
+    return out
+
+
 def cpu_baseline_leg(a):
     """rank 0, N=1 only: bounded sample (~10-20 s) of the same workload on the host cores"""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
@@ -591,6 +660,7 @@ def main():
         # next row: the updaters' depth hinge (yml: depth_min 1.0, lambda_depth 10) fused in
         line["with_depth_hinge"] = sweep(a, ctx_, sizes=((a.size, a.pairs),), hinge=(1.0, 10.0))[0]
         line["deepvoxels"] = deepvoxels_bench(ctx_)
+        line["deepvoxels_render_fused"] = render_bench(ctx_)
     if not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg(a)
     print(json.dumps(line), flush=True)

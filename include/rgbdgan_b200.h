@@ -219,6 +219,34 @@ RGBD_API int rgbd_dv_project_fwd(const rgbd_dv_params *p, const float *grid, con
 RGBD_API int rgbd_dv_project_bwd(const rgbd_dv_params *p, const float *g_frustum, const float *cam2world,
                         int B, int F, float *g_grid, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- "next" row: the per-sample render tail of DeepVoxels.forward with the shipped
+ *      `occlusion_type: accumulative` (deepvoxel.py:879-892,903-904 around AccumulativeOcclusionNet.forward,
+ *      :574-587), fused with the projection: the (B,F,D,H,W) canonical view volume is never materialised.
+ *      The occlusion module's two 1x1x1 EqualizedConv3d layers (deepvoxel.py:560-567, pggan.py:27-38) are
+ *      passed as plain arrays: W1 (nf, F+1) [input channel 0 = depth coordinate], b1 (nf), W2 (nf), b2 (1).   */
+typedef struct {
+    int nf;              /* occnet_nf; only 4 (deepvoxel.py:830) is built                                  */
+    int depth_steps;     /* int(ceil(sqrt(3) * grid_dims[-1])) of the depth rescale (:903), normally == D  */
+    float threshold;     /* accmulative_threshold (:556, default 4)                                        */
+    float inv_c1, inv_c2; /* EqualizedConv3d input scales sqrt(2) * sqrt(1 / in_ch) (pggan.py:31)           */
+} rgbd_dv_render_params;
+
+/* workspace: channels-last staging of a chunk of grids, the same for their gradients, weight-gradient partials */
+RGBD_API size_t rgbd_dv_render_workspace_bytes(const rgbd_dv_params *p, int B, int F);
+/* grid (B,F,G,G,G), cam2world (B,16) -> novel (B,F,H,W), depth (B,H,W) [rescaled, :903-904], fg (B,H,W) or NULL
+ * [= F.sum(weights, axis=2), the `foreground_weight` of :892].  F multiple of 4, F <= 32, D <= 128.            */
+RGBD_API int rgbd_dv_render_fwd(const rgbd_dv_params *p, const rgbd_dv_render_params *r, const float *grid,
+                       const float *cam2world, const float *W1, const float *b1, const float *W2, const float *b2,
+                       int B, int F, float *novel, float *depth, float *fg, void *workspace,
+                       size_t workspace_bytes, void *stream);
+/* its autograd by recomputation: upstream g_novel (B,F,H,W), g_depth (B,H,W), g_fg (B,H,W) or NULL ->
+ * g_grid (B,F,G,G,G), g_W1 (nf,F+1), g_b1 (nf), g_W2 (nf), g_b2 (1); all overwritten.                         */
+RGBD_API int rgbd_dv_render_bwd(const rgbd_dv_params *p, const rgbd_dv_render_params *r, const float *grid,
+                       const float *cam2world, const float *W1, const float *b1, const float *W2, const float *b2,
+                       int B, int F, const float *g_novel, const float *g_depth, const float *g_fg, float *g_grid,
+                       float *g_W1, float *g_b1, float *g_W2, float *g_b2, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

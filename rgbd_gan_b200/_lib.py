@@ -40,6 +40,11 @@ class DvParams(ctypes.Structure):
                 ("voxel_size", c_float), ("near_plane", c_float)]
 
 
+class DvRenderParams(ctypes.Structure):
+    """rgbd_dv_render_params"""
+    _fields_ = [("nf", c_int), ("depth_steps", c_int), ("threshold", c_float), ("inv_c1", c_float), ("inv_c2", c_float)]
+
+
 # name -> (restype, argtypes); must list every symbol the header declares (tests check this)
 SIGNATURES = {
     "rgbd_version": (c_int, []),
@@ -71,6 +76,11 @@ SIGNATURES = {
     "rgbd_dv_trilinear_bwd": (c_int, [c_void, c_void, c_void, c_int, c_int, c_int, ctypes.POINTER(DvParams), c_void,
                                       c_void]),
     "rgbd_dv_project_workspace_bytes": (c_size, [ctypes.POINTER(DvParams), c_int, c_int]),
+    "rgbd_dv_render_workspace_bytes": (c_size, [ctypes.POINTER(DvParams), c_int, c_int]),
+    "rgbd_dv_render_fwd": (c_int, [ctypes.POINTER(DvParams), ctypes.POINTER(DvRenderParams)] + [c_void] * 6 + [c_int, c_int] +
+                           [c_void] * 4 + [c_size, c_void]),
+    "rgbd_dv_render_bwd": (c_int, [ctypes.POINTER(DvParams), ctypes.POINTER(DvRenderParams)] + [c_void] * 6 + [c_int, c_int] +
+                           [c_void] * 9 + [c_size, c_void]),
     "rgbd_dv_project_fwd": (c_int, [ctypes.POINTER(DvParams), c_void, c_void, c_int, c_int, c_void, c_void, c_size,
                                     c_void]),
     "rgbd_dv_project_bwd": (c_int, [ctypes.POINTER(DvParams), c_void, c_void, c_int, c_int, c_void, c_void, c_size,

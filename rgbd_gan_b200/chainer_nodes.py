@@ -162,3 +162,52 @@ class LossFuncRotate:
         node = ConsistencyLoss(M, c, Mi, ci, opts, self._ws, self.grad_scale, xp=xp, lib=self._lib)
         loss, new_zp = node.apply((img, img_rot))
         return loss, new_zp
+
+
+class RenderAccumulative(FunctionNode):
+    """"Next" row: the per-sample loop of DeepVoxels.forward with `occlusion_type: accumulative`
+    (deepvoxel.py:879-892 + AccumulativeOcclusionNet.forward :574-587 + depth rescale :903-904) as one node.
+    inputs: (deepvoxels (B,F,G,G,G), W1 (nf,F+1), b1 (nf,), W2 (1,nf), b2 (1,)) -- the `.c.W` (1x1x1 kernels squeezed)
+    and `.c.b` of the two EqualizedConv3d of `occlusion_net.occlusion`; outputs: (novel_views (B,F,H,W),
+    depth_maps (B,1,H,W), foreground_weight (B,1,H,W))."""
+
+    def __init__(self, cam2world, dv_params, accmulative_threshold=4, xp=None, lib=None):
+        self.xp = xp if xp is not None else cupy
+        self.lib = lib if lib is not None else _lib
+        self.cam = self.xp.asarray(np.asarray(cam2world, dtype="float32").reshape(-1, 16), dtype="float32")
+        self.P, self.threshold = dv_params, float(accmulative_threshold)
+
+    def _rparams(self, F, nf):
+        return _lib.DvRenderParams(int(nf), int(np.ceil(np.sqrt(3) * self.P.G)), self.threshold,
+                                   float(np.float32(np.sqrt(2) * np.sqrt(1.0 / (F + 1)))),
+                                   float(np.float32(np.sqrt(2) * np.sqrt(1.0 / nf))))
+
+    def forward(self, inputs):
+        xp = self.xp
+        grid, W1, b1, W2, b2 = (xp.ascontiguousarray(a, dtype="float32") for a in inputs)
+        B, F = grid.shape[:2]
+        P = self.P
+        self.R = self._rparams(F, W1.shape[0])
+        self.ws = xp.empty(self.lib.load().rgbd_dv_render_workspace_bytes(ctypes.byref(P), B, F), dtype="uint8")
+        novel, depth, fg = xp.empty((B, F, P.H, P.W), "float32"), xp.empty((B, 1, P.H, P.W), "float32"), \
+            xp.empty((B, 1, P.H, P.W), "float32")
+        self.lib.call("rgbd_dv_render_fwd", ctypes.byref(P), ctypes.byref(self.R), _ptr(grid), _ptr(self.cam), _ptr(W1),
+                      _ptr(b1), _ptr(W2), _ptr(b2), B, F, _ptr(novel), _ptr(depth), _ptr(fg), _ptr(self.ws),
+                      int(self.ws.size), _stream(xp))
+        self.retain_inputs((0, 1, 2, 3, 4))
+        return novel, depth, fg
+
+    def backward(self, target_input_indexes, grad_outputs):
+        xp = self.xp
+        grid, W1, b1, W2, b2 = (xp.ascontiguousarray(v.array, dtype="float32") for v in self.get_retained_inputs())
+        B, F = grid.shape[:2]
+        P = self.P
+        arr = lambda g, shape: xp.zeros(shape, "float32") if g is None else xp.ascontiguousarray(
+            g.array if hasattr(g, "array") else g, dtype="float32")
+        g_novel, g_depth = arr(grad_outputs[0], (B, F, P.H, P.W)), arr(grad_outputs[1], (B, 1, P.H, P.W))
+        g_fg = None if grad_outputs[2] is None else arr(grad_outputs[2], (B, 1, P.H, P.W))
+        outs = [xp.empty_like(a) for a in (grid, W1, b1, W2, b2)]
+        self.lib.call("rgbd_dv_render_bwd", ctypes.byref(P), ctypes.byref(self.R), _ptr(grid), _ptr(self.cam), _ptr(W1),
+                      _ptr(b1), _ptr(W2), _ptr(b2), B, F, _ptr(g_novel), _ptr(g_depth), _ptr(g_fg),
+                      *[_ptr(o) for o in outs], _ptr(self.ws), int(self.ws.size), _stream(xp))
+        return tuple(_as_var(outs[i]) for i in target_input_indexes)

@@ -478,6 +478,392 @@ k_dv_compact(const rgbd_dv_params P, const float *__restrict__ cam2world, const 
     }
 }
 
+// ---------------------------------------------------------------- fused render tail ("next" row)
+// DeepVoxels.forward with `occlusion_type: accumulative` (deepvoxels_shapenet_car.yml:34), per sample:
+//     vol = interpolate_trilinear(...)                                         deepvoxel.py:880-884
+//     occ = sigmoid(conv1x1(leaky_relu(conv1x1(concat(depth_coords, vol)))) - threshold)   :560-567,:575-576 (per voxel MLP, F+1 -> 4 -> 1)
+//     c = cumsum_d(occ); w_d = clip(c_d,0,1) - clip(c_{d-1},0,1)               :579-582
+//     depth = sum_d depth_coords_d * w_d;  novel = sum_d w_d * vol_d;  fg = sum_d w_d         :583,:888,:892
+//     depth = (depth + 0.5) * D * voxel_size + near_plane                       :903-904
+// The reference materialises vol (B,F,D,H,W: 28-58 MB per sample) and a dozen temporaries of the same size; here a
+// ray is walked front to back by an 8-lane group (lane = feature quad) and nothing but the (F+2) output planes
+// is written.  A ray stops at the first depth with c > 1: every later weight is exactly 0 and the clip passes
+// no gradient there.  Coordinates and in-grid mask are the bit-exact recipe of compute_proj_idcs (dv_coords);
+// values are tolerance-checked (1e-5) against golden vectors produced by the reference's own forward().
+constexpr int kRenderMaxD = 128;
+constexpr int kRenderNf = 4;             // occnet_nf (deepvoxel.py:830)
+
+struct RenderW {                          // the occlusion MLP as seen by one lane (feature quad fq)
+    float w1q[kRenderNf][4];              // W1[j][1 + 4*fq + c]
+    float w1d[kRenderNf], b1[kRenderNf], w2[kRenderNf];   // W1[j][0], b1[j], W2[0][j]
+    float b2;
+};
+
+__device__ __forceinline__ RenderW render_load_w(const float *__restrict__ W1, const float *__restrict__ b1,
+                                                 const float *__restrict__ W2, const float *__restrict__ b2, int F, int fq)
+{
+    RenderW r;
+#pragma unroll
+    for (int j = 0; j < kRenderNf; ++j) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r.w1q[j][c] = (4 * fq + c < F) ? __ldg(W1 + j * (F + 1) + 1 + 4 * fq + c) : 0.0f;
+        r.w1d[j] = __ldg(W1 + j * (F + 1)); r.b1[j] = __ldg(b1 + j); r.w2[j] = __ldg(W2 + j);
+    }
+    r.b2 = __ldg(b2);
+    return r;
+}
+
+// sum over the 8 lanes of a feature-quad group (all 8 lanes get the result)
+__device__ __forceinline__ float group8_sum(float v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    return v;
+}
+
+// occlusion MLP of one voxel: a_j (pre-activation) and occ; x = inv_c1 * (depth_coord | features)   pggan.py:38
+__device__ __forceinline__ float render_mlp(const RenderW &w, const rgbd_dv_render_params &R, float4 feat, float dc,
+                                            float a[kRenderNf])
+{
+    const float x0 = R.inv_c1 * feat.x, x1 = R.inv_c1 * feat.y, x2 = R.inv_c1 * feat.z, x3 = R.inv_c1 * feat.w;
+    const float xd = R.inv_c1 * dc;
+    float s = w.b2;
+#pragma unroll
+    for (int j = 0; j < kRenderNf; ++j) {
+        float p = fmaf(w.w1q[j][3], x3, fmaf(w.w1q[j][2], x2, fmaf(w.w1q[j][1], x1, w.w1q[j][0] * x0)));
+        p = group8_sum(p);
+        const float aj = (p + w.w1d[j] * xd) + w.b1[j];
+        a[j] = aj;
+        const float h = aj < 0.0f ? 0.2f * aj : aj;                      // F.leaky_relu (slope 0.2)
+        s = fmaf(w.w2[j], R.inv_c2 * h, s);
+    }
+    s -= R.threshold;                                                    // :565
+    return tanhf(s * 0.5f) * 0.5f + 0.5f;                                // F.sigmoid as Chainer evaluates it
+}
+
+__device__ __forceinline__ float render_depth_coord(int d, int D)
+{
+    // np.arange(-D // 2, D // 2)[d] / D  (deepvoxel.py:568-569; -D // 2 is a floor division)
+    const int lo = -((D + 1) / 2);
+    return (float)((double)(lo + d) / (double)D);
+}
+
+struct RayTaps { int off[8]; float w[8]; int keep; float dc; };
+
+// taps of frustum element (d, row, col) for the lane that owns depth slot `d`; folded corner weights
+__device__ __forceinline__ void render_taps(const rgbd_dv_params &P, const Cam &T, int d, int pix, bool valid, int F,
+                                            RayTaps &t)
+{
+    float vc[3] = {0.f, 0.f, 0.f};
+    const bool keep = valid && d < P.D && dv_coords(P, T, d * (P.W * P.H) + pix, vc);
+    t.keep = keep ? 1 : 0;
+    t.dc = render_depth_coord(d, P.D);          // (a double division: once per chunk and lane, then shuffled)
+    if (keep) {
+        ElemTaps e;
+        dv_elem_taps(vc, P.G, F, e);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t.off[k] = e.off[k];
+        t.w[0] = (e.wx0 * e.wy0) * e.wz0; t.w[1] = (e.wx1 * e.wy0) * e.wz0; t.w[2] = (e.wx0 * e.wy1) * e.wz0;
+        t.w[3] = (e.wx0 * e.wy0) * e.wz1; t.w[4] = (e.wx1 * e.wy0) * e.wz1; t.w[5] = (e.wx0 * e.wy1) * e.wz1;
+        t.w[6] = (e.wx1 * e.wy1) * e.wz0; t.w[7] = (e.wx1 * e.wy1) * e.wz1;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t.off[k] = 0; t.w[k] = 0.0f; }
+    }
+}
+
+#ifndef RGBD_RENDER_MINBLK
+#define RGBD_RENDER_MINBLK 2
+#endif
+// one warp = 4 rays x 8 feature quads; block = 8 warps = 32 consecutive pixels
+__global__ void __launch_bounds__(32 * kDvWarps, RGBD_RENDER_MINBLK)
+k_dv_render_fwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const float *__restrict__ cl,
+                const float *__restrict__ cam2world, const float *__restrict__ W1, const float *__restrict__ b1,
+                const float *__restrict__ W2, const float *__restrict__ b2, int F, float *__restrict__ novel,
+                float *__restrict__ depth, float *__restrict__ fg)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int eg = lane >> 3, fq = lane & 7, gbase = lane & ~7;
+    const int b = blockIdx.y;
+    const int HW = P.W * P.H;
+    const int pix = (blockIdx.x * kDvWarps + wid) * 4 + eg;
+    const bool valid = pix < HW;
+    const Cam T = load_cam(cam2world + 16 * b);
+    const RenderW w = render_load_w(W1, b1, W2, b2, F, fq);
+    const size_t G3 = (size_t)P.G * P.G * P.G;
+    const float *__restrict__ src = cl + (size_t)b * G3 * F;
+    const int f = 4 * fq;
+    float c = 0.0f, clip_prev = 0.0f, dm = 0.0f, fgs = 0.0f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool done = !valid;
+    // (gathering the 8 steps of a chunk together before the MLPs and the scan was measured: no gain, the kernel
+    //  is bound by shuffle / issue throughput at 128 registers, not by the latency of the gathers)
+    for (int d0 = 0; d0 < P.D; d0 += 8) {
+        if (__all_sync(FULL, done)) break;                              // every ray of the warp is saturated
+        RayTaps mine;
+        render_taps(P, T, d0 + fq, pix, valid && !done, F, mine);       // lane fq prepares depth d0 + fq of its ray
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            const int d = d0 + q;
+            if (d >= P.D) break;                                        // warp-uniform
+            const int sl = gbase | q;
+            const int keep = __shfl_sync(FULL, mine.keep, sl);
+            int off[8];
+            float wk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { off[k] = __shfl_sync(FULL, mine.off[k], sl); wk[k] = __shfl_sync(FULL, mine.w[k], sl); }
+            float4 feat = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (keep && !done && f < F) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(src + (off[k] + f)));
+                    feat.x = fmaf(v.x, wk[k], feat.x); feat.y = fmaf(v.y, wk[k], feat.y);
+                    feat.z = fmaf(v.z, wk[k], feat.z); feat.w = fmaf(v.w, wk[k], feat.w);
+                }
+            }
+            const float dc = __shfl_sync(FULL, mine.dc, sl);
+            float a[kRenderNf];
+            const float occ = render_mlp(w, R, feat, dc, a);            // (shuffles: executed by every lane)
+            if (!done) {
+                c += occ;                                               // F.cumsum
+                const float clip = fminf(fmaxf(c, 0.0f), 1.0f);         // F.clip(., 0, 1)
+                const float wd = clip - clip_prev;                      // cumsum[1:] - cumsum[:-1]
+                clip_prev = clip;
+                acc.x = fmaf(wd, feat.x, acc.x); acc.y = fmaf(wd, feat.y, acc.y);
+                acc.z = fmaf(wd, feat.z, acc.z); acc.w = fmaf(wd, feat.w, acc.w);
+                dm = fmaf(dc, wd, dm);
+                fgs += wd;
+                if (c > 1.0f) done = true;                              // later weights are exactly 0
+            }
+        }
+    }
+    if (valid) {
+        float *o = novel + ((size_t)b * F + f) * HW + pix;
+        if (f + 0 < F) o[0] = acc.x;
+        if (f + 1 < F) o[(size_t)HW] = acc.y;
+        if (f + 2 < F) o[2 * (size_t)HW] = acc.z;
+        if (f + 3 < F) o[3 * (size_t)HW] = acc.w;
+        if (fq == 0) {
+            // ((depth + 0.5) * int(ceil(sqrt(3) G))) * voxel_size + near_plane, one fp32 rounding per step  :903-904
+            depth[(size_t)b * HW + pix] = __fadd_rn(__fmul_rn(__fmul_rn(__fadd_rn(dm, 0.5f), (float)R.depth_steps), P.voxel_size), P.near_plane);
+            if (fg) fg[(size_t)b * HW + pix] = fgs;
+        }
+    }
+}
+
+// Backward of the fused render tail by recomputation.  Pass 1 walks the ray front to back and keeps, per depth,
+// the running sum c_d and dL/dw_d in shared memory (2 x 4 B per depth step and ray); pass 2 walks back to front
+// with the suffix sum of dL/dc (backward of F.cumsum), re-gathers the features, back-propagates the occlusion
+// MLP (weight gradients accumulate in registers, reduced once per block) and scatters dL/dfeature into the
+// channels-last grid gradient with 16-byte REDs (the lift).  Depths behind the first c_d > 1 carry no gradient.
+__global__ void __launch_bounds__(32 * kDvWarps)
+k_dv_render_bwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const float *__restrict__ cl,
+                const float *__restrict__ cam2world, const float *__restrict__ W1, const float *__restrict__ b1,
+                const float *__restrict__ W2, const float *__restrict__ b2, int F, const float *__restrict__ g_novel,
+                const float *__restrict__ g_depth, const float *__restrict__ g_fg, float *__restrict__ gcl,
+                float *__restrict__ partials, int nvals)
+{
+    __shared__ float s_c[kDvWarps][4][kRenderMaxD];
+    __shared__ float s_gw[kDvWarps][4][kRenderMaxD + 1];
+    __shared__ float s_red[kDvWarps][kRenderNf * 33 + 2 * kRenderNf + 1];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int eg = lane >> 3, fq = lane & 7, gbase = lane & ~7;
+    const int b = blockIdx.y;
+    const int HW = P.W * P.H;
+    const int pix = (blockIdx.x * kDvWarps + wid) * 4 + eg;
+    const bool valid = pix < HW;
+    const Cam T = load_cam(cam2world + 16 * b);
+    const RenderW w = render_load_w(W1, b1, W2, b2, F, fq);
+    const size_t G3 = (size_t)P.G * P.G * P.G;
+    const float *__restrict__ src = cl + (size_t)b * G3 * F;
+    float *__restrict__ dst = gcl + (size_t)b * G3 * F;
+    const int f = 4 * fq;
+    float4 gcol = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gdm = 0.0f, gfg = 0.0f;
+    if (valid) {
+        const float *g = g_novel + ((size_t)b * F + f) * HW + pix;
+        if (f + 0 < F) gcol.x = __ldg(g);
+        if (f + 1 < F) gcol.y = __ldg(g + (size_t)HW);
+        if (f + 2 < F) gcol.z = __ldg(g + 2 * (size_t)HW);
+        if (f + 3 < F) gcol.w = __ldg(g + 3 * (size_t)HW);
+        gdm = (__ldg(g_depth + (size_t)b * HW + pix) * P.voxel_size) * (float)R.depth_steps;   // backward of :903-904
+        if (g_fg) gfg = __ldg(g_fg + (size_t)b * HW + pix);
+    }
+    float *sc = s_c[wid][eg], *sgw = s_gw[wid][eg];
+
+    // ---- pass 1: front to back
+    float c = 0.0f;
+    int nd = 0;                                                          // depth steps that matter for this ray
+    bool done = !valid;
+    for (int d0 = 0; d0 < P.D; d0 += 8) {
+        if (__all_sync(FULL, done)) break;
+        RayTaps mine;
+        render_taps(P, T, d0 + fq, pix, valid && !done, F, mine);
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            const int d = d0 + q;
+            if (d >= P.D) break;
+            const int sl = gbase | q;
+            const int keep = __shfl_sync(FULL, mine.keep, sl);
+            int off[8];
+            float wk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { off[k] = __shfl_sync(FULL, mine.off[k], sl); wk[k] = __shfl_sync(FULL, mine.w[k], sl); }
+            float4 feat = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (keep && !done && f < F) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(src + (off[k] + f)));
+                    feat.x = fmaf(v.x, wk[k], feat.x); feat.y = fmaf(v.y, wk[k], feat.y);
+                    feat.z = fmaf(v.z, wk[k], feat.z); feat.w = fmaf(v.w, wk[k], feat.w);
+                }
+            }
+            const float dc = __shfl_sync(FULL, mine.dc, sl);
+            float a[kRenderNf];
+            const float occ = render_mlp(w, R, feat, dc, a);
+            // dL/dw_d = <g_novel, feat_d> + g_depth_map * depth_coord_d + g_fg      (:583,:888,:892)
+            const float dot = group8_sum(fmaf(gcol.w, feat.w, fmaf(gcol.z, feat.z, fmaf(gcol.y, feat.y, gcol.x * feat.x))));
+            if (!done) {
+                c += occ;
+                if (fq == 0) { sc[d] = c; sgw[d] = fmaf(gdm, dc, dot) + gfg; }
+                nd = d + 1;
+                if (c > 1.0f) done = true;
+            }
+        }
+    }
+    if (fq == 0 && valid) sgw[nd] = 0.0f;                                // no weight behind the last step
+    __syncwarp();
+
+    // ---- pass 2: back to front
+    float gW1q[kRenderNf][4], gW1d[kRenderNf], gb1[kRenderNf], gW2[kRenderNf], gb2 = 0.0f;
+#pragma unroll
+    for (int j = 0; j < kRenderNf; ++j) {
+        gW1d[j] = gb1[j] = gW2[j] = 0.0f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) gW1q[j][cc] = 0.0f;
+    }
+    int ndmax = nd;
+    ndmax = max(ndmax, __shfl_xor_sync(FULL, ndmax, 8));
+    ndmax = max(ndmax, __shfl_xor_sync(FULL, ndmax, 16));
+    float S = 0.0f;                                                      // suffix sum of dL/dc (F.cumsum backward)
+    for (int d0 = ((ndmax - 1) >> 3) << 3; d0 >= 0; d0 -= 8) {
+        RayTaps mine;
+        render_taps(P, T, d0 + fq, pix, valid && (d0 + fq) < nd, F, mine);
+#pragma unroll 1
+        for (int q = 7; q >= 0; --q) {
+            const int d = d0 + q;
+            if (d >= ndmax) continue;                                    // warp-uniform
+            const bool active = valid && d < nd;
+            const int sl = gbase | q;
+            const int keep = __shfl_sync(FULL, mine.keep, sl);
+            int off[8];
+            float wk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { off[k] = __shfl_sync(FULL, mine.off[k], sl); wk[k] = __shfl_sync(FULL, mine.w[k], sl); }
+            float4 ft = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (keep && active && f < F) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(src + (off[k] + f)));
+                    ft.x = fmaf(v.x, wk[k], ft.x); ft.y = fmaf(v.y, wk[k], ft.y);
+                    ft.z = fmaf(v.z, wk[k], ft.z); ft.w = fmaf(v.w, wk[k], ft.w);
+                }
+            }
+            const float dc = __shfl_sync(FULL, mine.dc, sl);
+            float a[kRenderNf];
+            const float occ = render_mlp(w, R, ft, dc, a);
+            if (!active) continue;
+            const float cd = sc[d], cp = d > 0 ? sc[d - 1] : 0.0f;
+            const float wd = fminf(fmaxf(cd, 0.0f), 1.0f) - fminf(fmaxf(cp, 0.0f), 1.0f);
+            if (cd >= 0.0f && cd <= 1.0f) S += sgw[d] - sgw[d + 1];     // Clip backward (inclusive bounds), diff backward
+            const float gs = S * occ * (1.0f - occ);                     // Sigmoid backward
+            gb2 += gs;
+            float gx0 = 0.0f, gx1 = 0.0f, gx2 = 0.0f, gx3 = 0.0f;
+            const float x0 = R.inv_c1 * ft.x, x1 = R.inv_c1 * ft.y, x2 = R.inv_c1 * ft.z, x3 = R.inv_c1 * ft.w;
+            const float xd = R.inv_c1 * dc;
+#pragma unroll
+            for (int j = 0; j < kRenderNf; ++j) {
+                const float h = a[j] < 0.0f ? 0.2f * a[j] : a[j];
+                gW2[j] = fmaf(gs, R.inv_c2 * h, gW2[j]);
+                const float gh = (gs * w.w2[j]) * R.inv_c2;
+                const float ga = a[j] < 0.0f ? 0.2f * gh : gh;           // LeakyReLU backward
+                gb1[j] += ga;
+                gW1d[j] = fmaf(ga, xd, gW1d[j]);
+                gW1q[j][0] = fmaf(ga, x0, gW1q[j][0]); gW1q[j][1] = fmaf(ga, x1, gW1q[j][1]);
+                gW1q[j][2] = fmaf(ga, x2, gW1q[j][2]); gW1q[j][3] = fmaf(ga, x3, gW1q[j][3]);
+                gx0 = fmaf(ga, w.w1q[j][0], gx0); gx1 = fmaf(ga, w.w1q[j][1], gx1);
+                gx2 = fmaf(ga, w.w1q[j][2], gx2); gx3 = fmaf(ga, w.w1q[j][3], gx3);
+            }
+            if (keep && f < F) {
+                // dL/dfeat = w_d * g_novel + inv_c1 * W1^T ga, scattered to the 8 corners (interpolate_trilinear backward)
+                const float4 gf = make_float4(fmaf(wd, gcol.x, R.inv_c1 * gx0), fmaf(wd, gcol.y, R.inv_c1 * gx1),
+                                              fmaf(wd, gcol.z, R.inv_c1 * gx2), fmaf(wd, gcol.w, R.inv_c1 * gx3));
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    atomicAdd(reinterpret_cast<float4 *>(dst + (off[k] + f)),
+                              make_float4(gf.x * wk[k], gf.y * wk[k], gf.z * wk[k], gf.w * wk[k]));
+            }
+        }
+    }
+
+    // ---- weight gradients: sum over the 4 rays of the warp, then over the warps of the block
+    const int nW1 = kRenderNf * (F + 1);
+#pragma unroll
+    for (int j = 0; j < kRenderNf; ++j) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            float v = gW1q[j][cc];
+            v += __shfl_xor_sync(FULL, v, 8); v += __shfl_xor_sync(FULL, v, 16);
+            if (eg == 0 && f + cc < F) s_red[wid][j * (F + 1) + 1 + f + cc] = v;
+        }
+        float v0 = gW1d[j], v1 = gb1[j], v2 = gW2[j];
+        v0 += __shfl_xor_sync(FULL, v0, 8); v0 += __shfl_xor_sync(FULL, v0, 16);
+        v1 += __shfl_xor_sync(FULL, v1, 8); v1 += __shfl_xor_sync(FULL, v1, 16);
+        v2 += __shfl_xor_sync(FULL, v2, 8); v2 += __shfl_xor_sync(FULL, v2, 16);
+        if (lane == 0) { s_red[wid][j * (F + 1)] = v0; s_red[wid][nW1 + j] = v1; s_red[wid][nW1 + kRenderNf + j] = v2; }
+    }
+    {
+        float v = gb2;
+        v += __shfl_xor_sync(FULL, v, 8); v += __shfl_xor_sync(FULL, v, 16);
+        if (lane == 0) s_red[wid][nW1 + 2 * kRenderNf] = v;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nvals) {
+        float v = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kDvWarps; ++k) v += s_red[k][threadIdx.x];
+        partials[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * nvals + threadIdx.x] = v;
+    }
+}
+
+// fixed-order sum of the per-block weight-gradient partials: one block per value
+__global__ void __launch_bounds__(256)
+k_dv_render_wgrad(const float *__restrict__ partials, int nblocks, int nvals, int F, float *__restrict__ g_W1,
+                  float *__restrict__ g_b1, float *__restrict__ g_W2, float *__restrict__ g_b2)
+{
+    __shared__ double sh[256];
+    const int v = blockIdx.x;
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < nblocks; k += 256) acc += (double)partials[(size_t)k * nvals + v];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s2 = 128; s2 > 0; s2 >>= 1) {
+        if ((int)threadIdx.x < s2) sh[threadIdx.x] += sh[threadIdx.x + s2];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int nW1 = kRenderNf * (F + 1);
+        const float r = (float)sh[0];
+        if (v < nW1) g_W1[v] = r;
+        else if (v < nW1 + kRenderNf) g_b1[v - nW1] = r;
+        else if (v < nW1 + 2 * kRenderNf) g_W2[v - nW1 - kRenderNf] = r;
+        else g_b2[0] = r;
+    }
+}
+
 static bool dv_ok(const rgbd_dv_params *p)
 {
     return p && p->W > 0 && p->H > 0 && p->D > 0 && p->G > 1 && p->voxel_size > 0.0f && p->fx != 0.0f && p->fy != 0.0f;
@@ -645,6 +1031,99 @@ RGBD_API int rgbd_dv_project_bwd(const rgbd_dv_params *p, const float *g_frustum
         count_launch(2);
     }
     return check_launch("rgbd_dv_project_bwd");
+}
+
+static bool render_ok(const rgbd_dv_params *p, const rgbd_dv_render_params *r, int B, int F)
+{
+    if (!dv_ok(p) || !r || B <= 0 || F <= 0) { set_error("rgbd_dv_render: null pointer or bad params"); return false; }
+    if (r->nf != kRenderNf || (F & 3) || F > 32 || p->D > kRenderMaxD) {
+        set_error("rgbd_dv_render: built for occnet_nf == %d, F %% 4 == 0, F <= 32, D <= %d (got nf %d, F %d, D %d)",
+                  kRenderNf, kRenderMaxD, r->nf, F, p->D);
+        return false;
+    }
+    return true;
+}
+
+struct RenderWs { size_t cl, gcl, partials, total; int Bs, nblk, nvals; };
+
+static RenderWs render_ws(const rgbd_dv_params *p, int B, int F)
+{
+    RenderWs w;
+    const size_t per = (size_t)p->G * p->G * p->G * F * sizeof(float);
+    w.Bs = (int)dv_chunk_samples(p, B, F);
+    w.nblk = (p->W * p->H + 4 * kDvWarps - 1) / (4 * kDvWarps);
+    w.nvals = kRenderNf * (F + 1) + 2 * kRenderNf + 1;
+    w.cl = 0;
+    w.gcl = (w.Bs * per + 255) / 256 * 256;
+    w.partials = 2 * w.gcl;
+    w.total = w.partials + ((size_t)B * w.nblk * w.nvals * sizeof(float) + 255) / 256 * 256;
+    return w;
+}
+
+RGBD_API size_t rgbd_dv_render_workspace_bytes(const rgbd_dv_params *p, int B, int F)
+{
+    if (!dv_ok(p) || B <= 0 || F <= 0) return 0;
+    return render_ws(p, B, F).total;
+}
+
+RGBD_API int rgbd_dv_render_fwd(const rgbd_dv_params *p, const rgbd_dv_render_params *r, const float *grid,
+                       const float *cam2world, const float *W1, const float *b1, const float *W2, const float *b2,
+                       int B, int F, float *novel, float *depth, float *fg, void *workspace, size_t workspace_bytes,
+                       void *stream)
+{
+    if (!render_ok(p, r, B, F)) return RGBD_E_UNSUPPORTED;
+    if (!grid || !cam2world || !W1 || !b1 || !W2 || !b2 || !novel || !depth) {
+        set_error("rgbd_dv_render_fwd: null pointer");
+        return RGBD_E_ARG;
+    }
+    const RenderWs L = render_ws(p, B, F);
+    if (!workspace || workspace_bytes < L.total) { set_error("rgbd_dv_render_fwd: workspace too small"); return RGBD_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int G3 = p->G * p->G * p->G, HW = p->W * p->H;
+    float *cl = (float *)((char *)workspace + L.cl);
+    for (int b0 = 0; b0 < B; b0 += L.Bs) {
+        const int nb = (B - b0 < L.Bs) ? (B - b0) : L.Bs;
+        k_dv_to_cl<<<dim3((G3 + 31) / 32, (F + 31) / 32, nb), dim3(32, 8), 0, st>>>(grid + (size_t)b0 * F * G3, cl, F, G3);
+        k_dv_render_fwd<<<dim3(L.nblk, nb), 32 * kDvWarps, 0, st>>>(*p, *r, cl, cam2world + 16 * (size_t)b0, W1, b1, W2, b2, F,
+                                                                  novel + (size_t)b0 * F * HW, depth + (size_t)b0 * HW,
+                                                                  fg ? fg + (size_t)b0 * HW : nullptr);
+        count_launch(2);
+    }
+    return check_launch("rgbd_dv_render_fwd");
+}
+
+RGBD_API int rgbd_dv_render_bwd(const rgbd_dv_params *p, const rgbd_dv_render_params *r, const float *grid,
+                       const float *cam2world, const float *W1, const float *b1, const float *W2, const float *b2,
+                       int B, int F, const float *g_novel, const float *g_depth, const float *g_fg, float *g_grid,
+                       float *g_W1, float *g_b1, float *g_W2, float *g_b2, void *workspace, size_t workspace_bytes,
+                       void *stream)
+{
+    if (!render_ok(p, r, B, F)) return RGBD_E_UNSUPPORTED;
+    if (!grid || !cam2world || !W1 || !b1 || !W2 || !b2 || !g_novel || !g_depth || !g_grid || !g_W1 || !g_b1 || !g_W2 || !g_b2) {
+        set_error("rgbd_dv_render_bwd: null pointer");
+        return RGBD_E_ARG;
+    }
+    const RenderWs L = render_ws(p, B, F);
+    if (!workspace || workspace_bytes < L.total) { set_error("rgbd_dv_render_bwd: workspace too small"); return RGBD_E_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int G3 = p->G * p->G * p->G, HW = p->W * p->H;
+    float *cl = (float *)((char *)workspace + L.cl), *gcl = (float *)((char *)workspace + L.gcl);
+    float *partials = (float *)((char *)workspace + L.partials);
+    for (int b0 = 0; b0 < B; b0 += L.Bs) {
+        const int nb = (B - b0 < L.Bs) ? (B - b0) : L.Bs;
+        k_dv_to_cl<<<dim3((G3 + 31) / 32, (F + 31) / 32, nb), dim3(32, 8), 0, st>>>(grid + (size_t)b0 * F * G3, cl, F, G3);
+        cudaError_t e = cudaMemsetAsync(gcl, 0, sizeof(float) * (size_t)nb * F * G3, st);
+        if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
+        k_dv_render_bwd<<<dim3(L.nblk, nb), 32 * kDvWarps, 0, st>>>(
+            *p, *r, cl, cam2world + 16 * (size_t)b0, W1, b1, W2, b2, F, g_novel + (size_t)b0 * F * HW,
+            g_depth + (size_t)b0 * HW, g_fg ? g_fg + (size_t)b0 * HW : nullptr, gcl,
+            partials + (size_t)b0 * L.nblk * L.nvals, L.nvals);
+        k_dv_from_cl<<<dim3((G3 + 31) / 32, (F + 31) / 32, nb), dim3(32, 8), 0, st>>>(gcl, g_grid + (size_t)b0 * F * G3, F, G3);
+        count_launch(3);
+    }
+    k_dv_render_wgrad<<<L.nvals, 256, 0, st>>>(partials, B * L.nblk, L.nvals, F, g_W1, g_b1, g_W2, g_b2);
+    count_launch();
+    return check_launch("rgbd_dv_render_bwd");
 }
 
 }  // extern "C"

@@ -118,6 +118,63 @@ class ProjectionHelper:
         cam = _cam_to_device(cam2world, grid.device).reshape(grid.shape[0], 16)
         return _ProjectFn.apply(grid, cam, self.params())
 
+    def render_accumulative(self, grid, cam2world, W1, b1, W2, b2, accmulative_threshold=4,
+                            return_foreground_weight=False):
+        """"Next" row: what DeepVoxels.forward does per sample with `occlusion_type:
+        accumulative` (deepvoxel.py:879-892 + AccumulativeOcclusionNet.forward :574-587 + depth rescale :903-904),
+        for the whole batch in one fused pass that never materialises the (B,F,D,H,W) view volume.
+        grid (B,F,G,G,G); cam2world (B,4,4); W1 (nf,F+1), b1 (nf,), W2 (1,nf), b2 (1,): the `.c.W` / `.c.b` of
+        the two EqualizedConv3d layers of `occlusion_net.occlusion` (1x1x1 kernels squeezed; input channel 0 of
+        W1 is the depth coordinate, :575).  Returns (novel_views (B,F,H,W), depth_maps (B,1,H,W)[, foreground
+        weight (B,1,H,W)]); differentiable in grid and the four parameter arrays."""
+        grid = _dev_f32(grid, "grid")
+        B, F = grid.shape[:2]
+        cam = _cam_to_device(cam2world, grid.device).reshape(B, 16)
+        W1, b1, W2, b2 = (_dev_f32(t, n).contiguous() for t, n in ((W1, "W1"), (b1, "b1"), (W2, "W2"), (b2, "b2")))
+        nf = W1.shape[0]
+        if W1.shape[1] != F + 1 or W2.numel() != nf or b1.numel() != nf or b2.numel() != 1:
+            raise ValueError("W1 must be (nf, F+1), b1 (nf,), W2 (1, nf), b2 (1,)")
+        G = int(self.grid_dims[-1])
+        rp = _lib.DvRenderParams(int(nf), int(np.ceil(np.sqrt(3) * G)), float(accmulative_threshold),
+                                 float(np.float32(np.sqrt(2) * np.sqrt(1.0 / (F + 1)))),       # pggan.py:31 (ksize 1)
+                                 float(np.float32(np.sqrt(2) * np.sqrt(1.0 / nf))))
+        novel, depth, fg = _RenderFn.apply(grid, W1, b1, W2, b2, cam, self.params(), rp)
+        return (novel, depth, fg) if return_foreground_weight else (novel, depth)
+
+
+class _RenderFn(torch.autograd.Function):
+    """fused projection + accumulative render tail (rgbd_dv_render_fwd / _bwd)"""
+
+    @staticmethod
+    def forward(ctx, grid, W1, b1, W2, b2, cam, params, rparams):
+        B, F = grid.shape[:2]
+        dev = grid.device
+        novel = torch.empty((B, F, params.H, params.W), dtype=torch.float32, device=dev)
+        depth = torch.empty((B, 1, params.H, params.W), dtype=torch.float32, device=dev)
+        fg = torch.empty((B, 1, params.H, params.W), dtype=torch.float32, device=dev)
+        ws = torch.empty(_lib.load().rgbd_dv_render_workspace_bytes(ctypes.byref(params), B, F), dtype=torch.uint8, device=dev)
+        _lib.call("rgbd_dv_render_fwd", ctypes.byref(params), ctypes.byref(rparams), _ptr(grid), _ptr(cam), _ptr(W1),
+                  _ptr(b1), _ptr(W2), _ptr(b2), B, F, _ptr(novel), _ptr(depth), _ptr(fg), _ptr(ws), ws.numel(), _stream())
+        ctx.save_for_backward(grid, W1, b1, W2, b2, cam)
+        ctx.params, ctx.rparams, ctx.ws = params, rparams, ws
+        return novel, depth, fg
+
+    @staticmethod
+    def backward(ctx, g_novel, g_depth, g_fg):
+        grid, W1, b1, W2, b2, cam = ctx.saved_tensors
+        B, F = grid.shape[:2]
+        z = lambda g, like: torch.zeros_like(like) if g is None else g.to(torch.float32).contiguous()
+        g_novel = z(g_novel, torch.empty((B, F, ctx.params.H, ctx.params.W), device=grid.device))
+        g_depth = z(g_depth, torch.empty((B, 1, ctx.params.H, ctx.params.W), device=grid.device))
+        g_fg = None if g_fg is None else g_fg.to(torch.float32).contiguous()
+        g_grid = torch.empty_like(grid)
+        gW1, gb1, gW2, gb2 = torch.empty_like(W1), torch.empty_like(b1), torch.empty_like(W2), torch.empty_like(b2)
+        _lib.call("rgbd_dv_render_bwd", ctypes.byref(ctx.params), ctypes.byref(ctx.rparams), _ptr(grid), _ptr(cam),
+                  _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), B, F, _ptr(g_novel), _ptr(g_depth),
+                  None if g_fg is None else _ptr(g_fg), _ptr(g_grid), _ptr(gW1), _ptr(gb1), _ptr(gW2), _ptr(gb2),
+                  _ptr(ctx.ws), ctx.ws.numel(), _stream())
+        return g_grid, gW1, gb1, gW2, gb2, None, None, None
+
 
 class _TrilinearFn(torch.autograd.Function):
     @staticmethod

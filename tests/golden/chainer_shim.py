@@ -583,7 +583,71 @@ class MeanSquaredError(FunctionNode):
         return tuple(out[i] for i in idx)
 
 
+class Cumsum(FunctionNode):
+    """chainer.functions.cumsum (math/cumsum.py): forward xp.cumsum, backward flip(cumsum(flip(gy)))"""
+    def __init__(self, axis=None):
+        self.axis = axis
+
+    def forward(self, x):
+        return _force_array(numpy.cumsum(x[0], axis=self.axis), x[0].dtype),
+
+    def backward(self, idx, gy):
+        g = _arr(gy[0])
+        return _force_array(numpy.flip(numpy.cumsum(numpy.flip(g, self.axis), axis=self.axis), self.axis), g.dtype),
+
+
+class Sum(FunctionNode):
+    """chainer.functions.sum (math/sum.py): forward x.sum(axis), backward broadcast of gy"""
+    def __init__(self, axis=None, keepdims=False):
+        self.axis = axis if (axis is None or isinstance(axis, tuple)) else (axis,)
+        self.keepdims = keepdims
+
+    def forward(self, x):
+        self.in_shape = x[0].shape
+        return _force_array(x[0].sum(axis=self.axis, keepdims=self.keepdims), x[0].dtype),
+
+    def backward(self, idx, gy):
+        g = _arr(gy[0])
+        if not self.keepdims and self.axis is not None:
+            for a in sorted(ax % len(self.in_shape) for ax in self.axis):
+                g = numpy.expand_dims(g, a)
+        return numpy.ascontiguousarray(numpy.broadcast_to(g, self.in_shape)),
+
+
+class Sigmoid(FunctionNode):
+    """chainer.functions.sigmoid (activation/sigmoid.py): forward_cpu tanh(x*0.5)*0.5+0.5, backward gy*y*(1-y)"""
+    def forward(self, x):
+        half = x[0].dtype.type(0.5)
+        self.y = _force_array(numpy.tanh(x[0] * half) * half + half, x[0].dtype)
+        return self.y,
+
+    def backward(self, idx, gy):
+        one = self.y.dtype.type(1)
+        return _force_array(_arr(gy[0]) * self.y * (one - self.y), self.y.dtype),
+
+
+class LeakyReLU(FunctionNode):
+    """chainer.functions.leaky_relu (activation/leaky_relu.py): y = x; y[x < 0] *= slope; backward on y < 0"""
+    def __init__(self, slope=0.2):
+        self.slope = slope
+
+    def forward(self, x):
+        y = x[0].copy()
+        y[x[0] < 0] *= self.slope
+        self.y = y
+        return y,
+
+    def backward(self, idx, gy):
+        g = _arr(gy[0]).copy()
+        g[self.y < 0] *= self.slope
+        return g,
+
+
 functions = types.ModuleType("chainer.functions")
+functions.cumsum = lambda x, axis=None: Cumsum(axis).apply((x,))[0]
+functions.sum = lambda x, axis=None, keepdims=False: Sum(axis, keepdims).apply((x,))[0]
+functions.sigmoid = lambda x: Sigmoid().apply((x,))[0]
+functions.leaky_relu = lambda x, slope=0.2: LeakyReLU(slope).apply((x,))[0]
 functions.get_item = lambda x, slices: GetItem(slices).apply((x,))[0]
 functions.reshape = lambda x, shape: Reshape(shape).apply((x,))[0]
 functions.transpose = lambda x, axes=None: Transpose(axes).apply((x,))[0]

@@ -223,8 +223,81 @@ def dv_case(pj, dv, get_cam, Prior, name, seed, G, img, F, nsamp):
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
 
 
+def render_case(pj, dv, get_cam, Prior, name, seed, G, img, F, nsamp, nf=4, threshold=4):
+    """Next row: the per-sample render tail of DeepVoxels.forward with the shipped
+    `occlusion_type: accumulative` (deepvoxels_shapenet_car.yml:34):
+        can_view_vol = interpolate_trilinear(...)                        deepvoxel.py:880-884   (reference code, unmodified)
+        weights, depth_map = AccumulativeOcclusionNet.forward(vol)       deepvoxel.py:574-587   (reference code, unmodified)
+        collapsed = F.sum(weights * vol, axis=2); fg = F.sum(weights, 2) deepvoxel.py:888,892   (restated here)
+        depth = (depth + 0.5) * ceil(sqrt(3) G) * voxel_size + near      deepvoxel.py:903-904   (restated here)
+    `self.occlusion` (deepvoxel.py:560-567) is a chainer.Sequential of two Conv3dSame(kernel_size=1) =
+    EqualizedConv3d (pggan.py:27-38: conv(inv_c * x), inv_c = sqrt(2) * sqrt(1 / in_ch)) around leaky_relu,
+    `x - threshold`, sigmoid; the 1x1x1 convolutions are restated as channel matmuls over the shim."""
+    F_ = chainer.functions
+    np.random.seed(seed)
+    h, D, voxel_size, near_plane = dv_helper(pj, G, img)
+    thetas = Prior(Cfg(**DV_CAR)).sample(2 * ((nsamp + 1) // 2))[:nsamp]
+    cam = get_cam(thetas)
+    grid = np.random.normal(size=(nsamp, F, G, G, G)).astype("float32")
+    W1 = Variable(np.random.normal(size=(nf, F + 1)).astype("float32"))             # initialW = Normal(1.0)
+    b1 = Variable(np.random.normal(scale=0.3, size=(nf,)).astype("float32"))
+    W2 = Variable(np.random.normal(size=(1, nf)).astype("float32"))
+    b2 = Variable(np.random.normal(scale=0.3, size=(1,)).astype("float32"))
+    inv_c1 = np.sqrt(2) * np.sqrt(1.0 / (F + 1))                                    # pggan.py:31 (ksize = 1)
+    inv_c2 = np.sqrt(2) * np.sqrt(1.0 / nf)
+
+    def conv1x1(x, W, b, inv_c):
+        bsz, c = x.shape[0], x.shape[1]
+        sp = x.shape[2:]
+        xs = F_.reshape(inv_c * x, (bsz, c, -1))                                     # pggan.py:38  self.c(self.inv_c * x)
+        y = F_.matmul(W, xs)                                                         # 1x1x1 convolution
+        y = y + F_.reshape(b, (1, -1, 1))
+        return F_.reshape(y, (bsz, W.shape[0]) + tuple(sp))
+
+    def occlusion(x):                                                                # deepvoxel.py:560-567
+        hdn = F_.leaky_relu(conv1x1(x, W1, b1, inv_c1))
+        o = conv1x1(hdn, W2, b2, inv_c2)
+        return F_.sigmoid(o - threshold)
+
+    net = object.__new__(dv.AccumulativeOcclusionNet)                                # forward() is the reference's own
+    depth_coords = np.arange(-D // 2, D // 2)[None, None, :, None, None] / D         # deepvoxel.py:568-571
+    net.depth_coords = np.tile(depth_coords, (1, 1, 1, img, img)).astype("float32")
+    net.occlusion = occlusion
+    net.xp = np
+    voxels = Variable(grid.copy())
+    novel, depths, fgs = [], [], []
+    for i in range(nsamp):                                                           # deepvoxel.py:879-892
+        lin_ind, vc = h.compute_proj_idcs(cam[i])
+        vol = dv.interpolate_trilinear(voxels[None, i], lin_ind, vc, [img, img], D)
+        w, depth_map = dv.AccumulativeOcclusionNet.forward(net, vol)
+        novel.append(F_.reshape(F_.sum(w * vol, axis=2), (1, -1, img, img)))
+        depths.append(depth_map)
+        fgs.append(F_.sum(w, axis=2))
+    novel = F_.concat(novel, axis=0)
+    depth = F_.concat(depths, axis=0)
+    fg = F_.concat(fgs, axis=0)
+    depth = ((depth + 0.5) * int(np.ceil(np.sqrt(3) * G)) * voxel_size + near_plane)  # deepvoxel.py:903-904
+    g_novel = np.random.normal(size=novel.shape).astype("float32")
+    g_depth = np.random.normal(size=depth.shape).astype("float32")
+    g_fg = np.random.normal(size=fg.shape).astype("float32")
+    loss = F_.sum(novel * g_novel) + F_.sum(depth * g_depth) + F_.sum(fg * g_fg)
+    loss.backward()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), G=G, img=img, F=F, D=D, nf=nf, threshold=threshold,
+                        voxel_size=voxel_size, near_plane=near_plane, thetas=thetas, cam=cam, grid=grid,
+                        intrinsic=dv_intrinsic(img), W1=W1.array, b1=b1.array, W2=W2.array, b2=b2.array,
+                        inv_c1=inv_c1, inv_c2=inv_c2, novel=novel.array, depth=depth.array, fg=fg.array,
+                        g_novel=g_novel, g_depth=g_depth, g_fg=g_fg, g_grid=voxels.grad, g_W1=W1.grad, g_b1=b1.grad,
+                        g_W2=W2.grad, g_b2=b2.grad)
+    print("%-22s novel |max| %.4g  depth range [%.4g, %.4g]  fg range [%.3g, %.3g]" % (
+        name, np.abs(novel.array).max(), depth.array.min(), depth.array.max(), fg.array.min(), fg.array.max()))
+
+
 def main():
     lf, pj, dv, get_cam, Prior = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "render":     # only the render-tail cases (leaves the other files untouched)
+        render_case(pj, dv, get_cam, Prior, "render_g16", 20, G=16, img=32, F=32, nsamp=2)
+        render_case(pj, dv, get_cam, Prior, "render_g12_thr3", 21, G=12, img=24, F=32, nsamp=3, threshold=3)
+        return
     c = lambda *a, **k: consistency_case(lf, get_cam, Prior, *a, **k)
     # cfg0 / cfg1 shape (BASELINE.json configs[0], [1]) at B=2
     c("loss_cfg0_l1_occ", 0, B=2, C=4, S=128, depth="rough", pose=FFHQ, occ=True, lam=3)
@@ -250,6 +323,9 @@ def main():
     # production geometry (deepvoxels_generator.py:229-253) with one feature
     dv_case(pj, dv, get_cam, Prior, "dv_g16_f3", 10, G=16, img=32, F=3, nsamp=2)
     dv_case(pj, dv, get_cam, Prior, "dv_g32_f1", 11, G=32, img=64, F=1, nsamp=1)
+    # next row: DeepVoxels render tail with the accumulative occlusion module
+    render_case(pj, dv, get_cam, Prior, "render_g16", 20, G=16, img=32, F=32, nsamp=2)
+    render_case(pj, dv, get_cam, Prior, "render_g12_thr3", 21, G=12, img=24, F=32, nsamp=3, threshold=3)
 
 
 if __name__ == "__main__":

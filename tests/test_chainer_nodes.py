@@ -79,7 +79,8 @@ class OracleBackedLib:
         self.oracle, self.calls = oracle, []
 
     def load(self):
-        return types.SimpleNamespace(rgbd_consistency_workspace_bytes=lambda B, C, H, W: 1024)
+        return types.SimpleNamespace(rgbd_consistency_workspace_bytes=lambda B, C, H, W: 1024,
+                                     rgbd_dv_render_workspace_bytes=lambda P, B, F: 1024)
 
     def _common(self, a):
         img, img_rot, M, c, Mi, ci, B, C, H, W, opts = a[:11]
@@ -146,6 +147,27 @@ class OracleBackedLib:
             if r != 1.0:
                 _view(g0, (n,))[...] *= r
                 _view(g1, (n,))[...] *= r
+        elif name in ("rgbd_dv_render_fwd", "rgbd_dv_render_bwd"):
+            P, R = a[0]._obj, a[1]._obj
+            B, F = a[8], a[9]
+            G, HW = P.G, P.H * P.W
+            K = np.array([[P.fx, 0, P.cx, 0], [0, P.fy, P.cy, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+            P0 = self.oracle.dv_params(P.W, P.H, P.D, G, K, P.voxel_size, P.near_plane)
+            grid, cam = _view(a[2], (B, F, G, G, G)), _view(a[3], (B, 4, 4))
+            W1, b1, W2, b2 = _view(a[4], (R.nf, F + 1)), _view(a[5], (R.nf,)), _view(a[6], (1, R.nf)), _view(a[7], (1,))
+            args = (P0, grid, cam, W1, b1, W2, b2, R.threshold, R.inv_c1, R.inv_c2, R.depth_steps)
+            if name == "rgbd_dv_render_fwd":
+                assert len(a) == 16
+                novel, depth, fg = self.oracle.dv_render_fwd(*args)
+                _view(a[10], (B, F, HW))[...] = novel.reshape(B, F, HW)
+                _view(a[11], (B, HW))[...] = depth.reshape(B, HW)
+                _view(a[12], (B, HW))[...] = fg.reshape(B, HW)
+            else:
+                assert len(a) == 21
+                g_fg = _view(a[12], (B, P.H, P.W))
+                outs = self.oracle.dv_render_bwd(*args, _view(a[10], (B, F, P.H, P.W)), _view(a[11], (B, P.H, P.W)), g_fg)
+                for ptr, o in zip(a[13:18], outs):
+                    _view(ptr, o.shape)[...] = o
         else:
             raise AssertionError("unexpected C-ABI call " + name)
 
@@ -203,3 +225,26 @@ def test_chainer_node_with_fused_depth_hinge(nodes, oracle_mod, grad_scale):
     assert abs(float(loss.array) - float(g["total"])) <= 1e-5 * abs(float(g["total"]))
     assert_grad_close(np.asarray(img.grad), g["g_img"])
     assert_grad_close(np.asarray(img_rot.grad), g["g_img_rot"])
+
+
+@pytest.mark.parametrize("name", ["render_g12_thr3"])
+def test_chainer_render_node(nodes, oracle_mod, name):
+    """next row: RenderAccumulative.apply((deepvoxels, W1, b1, W2, b2)) + backward through the shim"""
+    from rgbd_gan_b200._lib import DvParams
+    g = load_golden(name)
+    G, img, D = int(g["G"]), int(g["img"]), int(g["D"])
+    P = DvParams(img, img, D, G, 2. * img, 2. * img, img / 2., img / 2., float(np.float32(g["voxel_size"])),
+                 float(np.float32(g["near_plane"])))
+    lib = OracleBackedLib(oracle_mod)
+    node = nodes.RenderAccumulative(g["cam"], P, float(g["threshold"]), xp=FakeXP(), lib=lib)
+    V = chainer_shim.Variable
+    ins = [V(_wrap(g[k])) for k in ("grid", "W1", "b1", "W2", "b2")]
+    novel, depth, fg = node.apply(tuple(ins))
+    F_ = chainer_shim.functions
+    loss = F_.sum(novel * g["g_novel"]) + F_.sum(depth * g["g_depth"]) + F_.sum(fg * g["g_fg"])
+    loss.backward()
+    rel = lambda a, b: float(np.abs(np.asarray(a) - b).max() / np.abs(b).max())
+    assert rel(novel.array, g["novel"]) <= 1e-5 and rel(depth.array, g["depth"]) <= 1e-5
+    for v, key in zip(ins, ("g_grid", "g_W1", "g_b1", "g_W2", "g_b2")):
+        assert rel(np.asarray(v.grad).reshape(g[key].shape), g[key]) <= 1e-5, key
+    assert lib.calls == ["rgbd_dv_render_fwd", "rgbd_dv_render_bwd"]

@@ -195,3 +195,25 @@ def test_depth_hinge_next_row(name, oracle_mod):
     gi2, gr2 = port.backward(gy)
     assert_grad_close(gi2 + gx[:B], g["g_img"])
     assert_grad_close(gr2 + gx[B:], g["g_img_rot"])
+
+
+RENDER_CASES = ["render_g16", "render_g12_thr3"]
+
+
+@pytest.mark.parametrize("name", RENDER_CASES)
+def test_render_tail_oracle_against_reference_golden(name, oracle_mod):
+    """next row: the closed-form NumPy restatement of the accumulative render tail against vectors
+    produced by the reference's own interpolate_trilinear + AccumulativeOcclusionNet.forward over the shim"""
+    g = load_golden(name)
+    G, img, D = int(g["G"]), int(g["img"]), int(g["D"])
+    P = oracle_mod.dv_params(img, img, D, G, g["intrinsic"], float(g["voxel_size"]), float(g["near_plane"]))
+    args = (P, g["grid"], g["cam"], g["W1"], g["b1"], g["W2"], g["b2"], float(g["threshold"]), float(g["inv_c1"]),
+            float(g["inv_c2"]), D)
+    novel, depth, fg = oracle_mod.dv_render_fwd(*args)
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    assert rel(novel, g["novel"]) <= 1e-5
+    assert rel(depth.reshape(g["depth"].shape), g["depth"]) <= 1e-6
+    assert rel(fg.reshape(g["fg"].shape), g["fg"]) <= 1e-5
+    gg, gW1, gb1, gW2, gb2 = oracle_mod.dv_render_bwd(*args, g["g_novel"], g["g_depth"], g["g_fg"])
+    for got, key in ((gg, "g_grid"), (gW1, "g_W1"), (gb1, "g_b1"), (gW2, "g_W2"), (gb2, "g_b2")):
+        assert rel(got.reshape(g[key].shape), g[key]) <= 1e-5, key
