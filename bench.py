@@ -574,18 +574,20 @@ def render_bench(ctx_):
         g_novel, g_depth = torch.randn_like(novel), torch.randn_like(depth)
         gW1, gb1, gW2, gb2 = torch.empty_like(W1), torch.empty_like(b1), torch.empty_like(W2), torch.empty_like(b2)
         ws = torch.empty(lib.rgbd_dv_render_workspace_bytes(ctypes.byref(P), B, F), dtype=torch.uint8, device=dev)
+        saved = torch.empty(lib.rgbd_dv_render_saved_bytes(ctypes.byref(P), B), dtype=torch.uint8, device=dev)
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         pw = [ctypes.c_void_p(t.data_ptr()) for t in (W1, b1, W2, b2)]
 
         def fwd(k):
             _lib.call("rgbd_dv_render_fwd", ctypes.byref(P), ctypes.byref(R), ctypes.c_void_p(grids[k % n_sets].data_ptr()),
                       ctypes.c_void_p(cam.data_ptr()), *pw, B, F, ctypes.c_void_p(novel.data_ptr()),
-                      ctypes.c_void_p(depth.data_ptr()), ctypes.c_void_p(fg.data_ptr()), ctypes.c_void_p(ws.data_ptr()),
-                      ws.numel(), st)
+                      ctypes.c_void_p(depth.data_ptr()), ctypes.c_void_p(fg.data_ptr()), ctypes.c_void_p(saved.data_ptr()),
+                      ctypes.c_void_p(ws.data_ptr()), ws.numel(), st)
 
         def bwd(k):
             _lib.call("rgbd_dv_render_bwd", ctypes.byref(P), ctypes.byref(R), ctypes.c_void_p(grids[k % n_sets].data_ptr()),
-                      ctypes.c_void_p(cam.data_ptr()), *pw, B, F, ctypes.c_void_p(g_novel.data_ptr()),
+                      ctypes.c_void_p(cam.data_ptr()), *pw, B, F, ctypes.c_void_p(saved.data_ptr()),
+                      ctypes.c_void_p(g_novel.data_ptr()),
                       ctypes.c_void_p(g_depth.data_ptr()), None, ctypes.c_void_p(ggs[k % n_sets].data_ptr()),
                       *[ctypes.c_void_p(t.data_ptr()) for t in (gW1, gb1, gW2, gb2)], ctypes.c_void_p(ws.data_ptr()),
                       ws.numel(), st)
@@ -602,15 +604,90 @@ def render_bench(ctx_):
             torch.cuda.synchronize(dev)
             return e0.elapsed_time(e1) / reps
 
-        ms_f, ms_b = timeit(fwd), timeit(bwd)
+        # (bwd(k) reads the running sums left by fwd(k): time the pair, then the forward alone)
+        ms_f = timeit(fwd)
+        ms_fb = timeit(lambda k: (fwd(k), bwd(k)))
+        ms_b = ms_fb - ms_f
         alg = 2 * (F * G ** 3 + (F + 2) * img * img) * 4 * B
         gbs = alg / ((ms_f + ms_b) * 1e-3) / 1e9
-        out.append({"G": G, "F": F, "frustum": [D, img, img], "batch": B, "fwd_ms": ms_f, "bwd_ms": ms_b,
-                    "samples_per_s": B / ((ms_f + ms_b) * 1e-3), "algorithmic_GBps": gbs,
-                    "frac_of_hbm_peak": gbs / ctx_["hbm_peak"], "saturated_rays": float((fg > 0.999999).float().mean().item())})
+        row = {"G": G, "F": F, "frustum": [D, img, img], "batch": B, "fwd_ms": ms_f, "bwd_ms": ms_b,
+               "samples_per_s": B / ((ms_f + ms_b) * 1e-3), "algorithmic_GBps": gbs,
+               "frac_of_hbm_peak": gbs / ctx_["hbm_peak"], "saturated_rays": float((fg > 0.999999).float().mean().item())}
+        # context: the same math as the reference's op chain (deepvoxel.py:574-587,888,903-904), UNFUSED, on this GPU:
+        # our projection kernel for the view volume, then library (PyTorch) elementwise / einsum / cumsum ops + autograd
+        try:
+            from rgbd_gan_b200.projection import _ProjectFn
+            dc = torch.from_numpy((np.arange(-D // 2, D // 2) / D).astype(np.float32)).to(dev)
+
+            def unfused(k, backward):
+                g = grids[k % n_sets].detach().requires_grad_(backward)
+                vol = _ProjectFn.apply(g, cam, P)
+                x = torch.cat([dc.view(1, 1, D, 1, 1).expand(B, 1, D, img, img), vol], 1) * R.inv_c1
+                a = torch.einsum("jc,bcdhw->bjdhw", W1, x) + b1.view(1, -1, 1, 1, 1)
+                h = torch.nn.functional.leaky_relu(a, 0.2)
+                sg = torch.sigmoid(torch.einsum("j,bjdhw->bdhw", W2, R.inv_c2 * h) + b2 - R.threshold)
+                cl = torch.clamp(torch.cumsum(sg, 1), 0, 1)
+                w = torch.diff(torch.cat([torch.zeros_like(cl[:, :1]), cl], 1), dim=1)
+                dm = ((dc.view(1, D, 1, 1) * w).sum(1) + 0.5) * D * P.voxel_size + P.near_plane
+                nv = (w[:, None] * vol).sum(2)
+                if backward:
+                    ((nv * g_novel.view_as(nv)).sum() + (dm * g_depth.view_as(dm)).sum()).backward()
+
+            row["unfused_torch_fwd_ms"] = timeit(lambda k: unfused(k, False), reps=3)
+            row["unfused_torch_fwd_bwd_ms"] = timeit(lambda k: unfused(k, True), reps=3)
+            row["fused_speedup_fwd_bwd"] = row["unfused_torch_fwd_bwd_ms"] / (ms_f + ms_b)
+        except Exception as e:           # noqa: BLE001  (context only; never fails the bench)
+            row["unfused_torch_error"] = repr(e)[:200]
+        out.append(row)
         del grids, ggs
         torch.cuda.empty_cache()
     return out
+
+
+def feature_consistency_bench(a, ctx_):
+    """the feature-space consistency loss of updater.py:345-354 (norm l2, C = 256 features +
+    1 depth at 32x32, yml batch 32 -> 16 pairs); runs through the generic-C kernels (not tuned)."""
+    import torch
+    from rgbd_gan_b200 import _lib, poses
+    from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
+    dev, lib = ctx_["dev"], ctx_["lib"]
+    B, C, S = 16, 257, 32
+    HW = S * S
+    rng = np.random.default_rng(0)
+    _, cam = poses.synthetic_batch(B, S, depth="rough", seed=3)
+    x = rng.uniform(-1, 1, size=(2 * B, C, S, S)).astype(np.float32)
+    x[:, -1] = rng.uniform(0.7, 1.5, size=(2 * B, S, S))
+    hf = LossFuncRotate(None, lambda_geometric=LAMBDA_GEO)
+    hf.init_params(None, size=S)
+    M, c, Mi, ci = pose_algebra(hf.K, hf.inv_K, cam[:B], cam[B:])
+    pv = torch.from_numpy(np.concatenate([M.reshape(-1), c.reshape(-1), Mi.reshape(-1), ci.reshape(-1)])).to(dev)
+    xt = torch.from_numpy(x).to(dev)
+    img, rot = xt[:B].contiguous(), xt[B:].contiguous()
+    g0, g1, parts = torch.empty_like(img), torch.empty_like(rot), torch.zeros(8, device=dev)
+    ws = torch.empty(lib.rgbd_consistency_workspace_bytes(B, C, S, S), dtype=torch.uint8, device=dev)
+    opts = _lib.LossOpts(_lib.NORM_L2, 1, float("nan"), float("nan"), LAMBDA_GEO, B, None)
+    pp = [ctypes.c_void_p(pv.data_ptr() + 4 * o) for o in (0, 9 * B, 12 * B, 21 * B)]
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def step():
+        _lib.call("rgbd_consistency_fwd_bwd", ctypes.c_void_p(img.data_ptr()), ctypes.c_void_p(rot.data_ptr()), *pp, B, C, S, S,
+                  ctypes.byref(opts), ctypes.c_float(LAMBDA_ROTATE), ctypes.c_void_p(parts.data_ptr()), None,
+                  ctypes.c_void_p(g0.data_ptr()), ctypes.c_void_p(g1.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(), st)
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 100
+    for _ in range(n):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / n
+    gbs = 24 * C * HW * B / (ms * 1e-3) / 1e9
+    return {"pairs": B, "channels": C, "size": S, "norm": "l2", "ms_per_step": ms, "pairs_per_s": B / (ms * 1e-3),
+            "step_algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / ctx_["hbm_peak"],
+            "note": "L2-resident (34 MB of inputs, re-used every step): context only"}
 
 
 def cpu_baseline_leg(a):
@@ -661,6 +738,7 @@ def main():
         line["with_depth_hinge"] = sweep(a, ctx_, sizes=((a.size, a.pairs),), hinge=(1.0, 10.0))[0]
         line["deepvoxels"] = deepvoxels_bench(ctx_)
         line["deepvoxels_render_fused"] = render_bench(ctx_)
+        line["feature_consistency_c257"] = feature_consistency_bench(a, ctx_)
     if not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg(a)
     print(json.dumps(line), flush=True)

@@ -235,17 +235,21 @@ typedef struct {
 RGBD_API size_t rgbd_dv_render_workspace_bytes(const rgbd_dv_params *p, int B, int F);
 /* grid (B,F,G,G,G), cam2world (B,16) -> novel (B,F,H,W), depth (B,H,W) [rescaled, :903-904], fg (B,H,W) or NULL
  * [= F.sum(weights, axis=2), the `foreground_weight` of :892].  F multiple of 4, F <= 32, D <= 128.            */
+/* saved (nullable, rgbd_dv_render_saved_bytes = B*H*W*(D+1)*4): the running sums c_d of every ray, kept for the
+ * backward pass (4 B per depth step where the reference keeps the F*4 B view volume and its temporaries).         */
+RGBD_API size_t rgbd_dv_render_saved_bytes(const rgbd_dv_params *p, int B);
 RGBD_API int rgbd_dv_render_fwd(const rgbd_dv_params *p, const rgbd_dv_render_params *r, const float *grid,
                        const float *cam2world, const float *W1, const float *b1, const float *W2, const float *b2,
-                       int B, int F, float *novel, float *depth, float *fg, void *workspace,
+                       int B, int F, float *novel, float *depth, float *fg, float *saved, void *workspace,
                        size_t workspace_bytes, void *stream);
 /* its autograd by recomputation: upstream g_novel (B,F,H,W), g_depth (B,H,W), g_fg (B,H,W) or NULL ->
- * g_grid (B,F,G,G,G), g_W1 (nf,F+1), g_b1 (nf), g_W2 (nf), g_b2 (1); all overwritten.                         */
+ * g_grid (B,F,G,G,G), g_W1 (nf,F+1), g_b1 (nf), g_W2 (nf), g_b2 (1); all overwritten.  saved: what the forward
+ * call for the SAME inputs wrote, or NULL (the kernel then repeats the forward walk first).                      */
 RGBD_API int rgbd_dv_render_bwd(const rgbd_dv_params *p, const rgbd_dv_render_params *r, const float *grid,
                        const float *cam2world, const float *W1, const float *b1, const float *W2, const float *b2,
-                       int B, int F, const float *g_novel, const float *g_depth, const float *g_fg, float *g_grid,
-                       float *g_W1, float *g_b1, float *g_W2, float *g_b2, void *workspace, size_t workspace_bytes,
-                       void *stream);
+                       int B, int F, const float *saved, const float *g_novel, const float *g_depth, const float *g_fg,
+                       float *g_grid, float *g_W1, float *g_b1, float *g_W2, float *g_b2, void *workspace,
+                       size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -77,10 +77,11 @@ SIGNATURES = {
                                       c_void]),
     "rgbd_dv_project_workspace_bytes": (c_size, [ctypes.POINTER(DvParams), c_int, c_int]),
     "rgbd_dv_render_workspace_bytes": (c_size, [ctypes.POINTER(DvParams), c_int, c_int]),
+    "rgbd_dv_render_saved_bytes": (c_size, [ctypes.POINTER(DvParams), c_int]),
     "rgbd_dv_render_fwd": (c_int, [ctypes.POINTER(DvParams), ctypes.POINTER(DvRenderParams)] + [c_void] * 6 + [c_int, c_int] +
-                           [c_void] * 4 + [c_size, c_void]),
+                           [c_void] * 5 + [c_size, c_void]),
     "rgbd_dv_render_bwd": (c_int, [ctypes.POINTER(DvParams), ctypes.POINTER(DvRenderParams)] + [c_void] * 6 + [c_int, c_int] +
-                           [c_void] * 9 + [c_size, c_void]),
+                           [c_void] * 10 + [c_size, c_void]),
     "rgbd_dv_project_fwd": (c_int, [ctypes.POINTER(DvParams), c_void, c_void, c_int, c_int, c_void, c_void, c_size,
                                     c_void]),
     "rgbd_dv_project_bwd": (c_int, [ctypes.POINTER(DvParams), c_void, c_void, c_int, c_int, c_void, c_void, c_size,

@@ -191,9 +191,10 @@ class RenderAccumulative(FunctionNode):
         self.ws = xp.empty(self.lib.load().rgbd_dv_render_workspace_bytes(ctypes.byref(P), B, F), dtype="uint8")
         novel, depth, fg = xp.empty((B, F, P.H, P.W), "float32"), xp.empty((B, 1, P.H, P.W), "float32"), \
             xp.empty((B, 1, P.H, P.W), "float32")
+        self.saved = xp.empty((B * P.H * P.W * (P.D + 1),), "float32")    # running sums of every ray, for backward
         self.lib.call("rgbd_dv_render_fwd", ctypes.byref(P), ctypes.byref(self.R), _ptr(grid), _ptr(self.cam), _ptr(W1),
-                      _ptr(b1), _ptr(W2), _ptr(b2), B, F, _ptr(novel), _ptr(depth), _ptr(fg), _ptr(self.ws),
-                      int(self.ws.size), _stream(xp))
+                      _ptr(b1), _ptr(W2), _ptr(b2), B, F, _ptr(novel), _ptr(depth), _ptr(fg), _ptr(self.saved),
+                      _ptr(self.ws), int(self.ws.size), _stream(xp))
         self.retain_inputs((0, 1, 2, 3, 4))
         return novel, depth, fg
 
@@ -208,6 +209,6 @@ class RenderAccumulative(FunctionNode):
         g_fg = None if grad_outputs[2] is None else arr(grad_outputs[2], (B, 1, P.H, P.W))
         outs = [xp.empty_like(a) for a in (grid, W1, b1, W2, b2)]
         self.lib.call("rgbd_dv_render_bwd", ctypes.byref(P), ctypes.byref(self.R), _ptr(grid), _ptr(self.cam), _ptr(W1),
-                      _ptr(b1), _ptr(W2), _ptr(b2), B, F, _ptr(g_novel), _ptr(g_depth), _ptr(g_fg),
+                      _ptr(b1), _ptr(W2), _ptr(b2), B, F, _ptr(self.saved), _ptr(g_novel), _ptr(g_depth), _ptr(g_fg),
                       *[_ptr(o) for o in outs], _ptr(self.ws), int(self.ws.size), _stream(xp))
         return tuple(_as_var(outs[i]) for i in target_input_indexes)

@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(32 * kDvWarps, RGBD_RENDER_MINBLK)
 k_dv_render_fwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const float *__restrict__ cl,
                 const float *__restrict__ cam2world, const float *__restrict__ W1, const float *__restrict__ b1,
                 const float *__restrict__ W2, const float *__restrict__ b2, int F, float *__restrict__ novel,
-                float *__restrict__ depth, float *__restrict__ fg)
+                float *__restrict__ depth, float *__restrict__ fg, float *__restrict__ saved)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -598,6 +598,10 @@ k_dv_render_fwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const flo
     float c = 0.0f, clip_prev = 0.0f, dm = 0.0f, fgs = 0.0f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     bool done = !valid;
+    int nd = 0;
+    // state for the backward pass (optional): per ray [nd | c_0 .. c_{D-1}], 4 B per depth step instead of the
+    // reference's F*4 B view volume; lets the backward skip its front-to-back recomputation pass
+    float *sv = saved ? saved + ((size_t)b * HW + (valid ? pix : 0)) * (P.D + 1) : nullptr;
     // (gathering the 8 steps of a chunk together before the MLPs and the scan was measured: no gain, the kernel
     //  is bound by shuffle / issue throughput at 128 registers, not by the latency of the gathers)
     for (int d0 = 0; d0 < P.D; d0 += 8) {
@@ -635,10 +639,13 @@ k_dv_render_fwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const flo
                 acc.z = fmaf(wd, feat.z, acc.z); acc.w = fmaf(wd, feat.w, acc.w);
                 dm = fmaf(dc, wd, dm);
                 fgs += wd;
+                nd = d + 1;
+                if (sv && fq == 0) sv[1 + d] = c;
                 if (c > 1.0f) done = true;                              // later weights are exactly 0
             }
         }
     }
+    if (sv && valid && fq == 0) sv[0] = __int_as_float(nd);
     if (valid) {
         float *o = novel + ((size_t)b * F + f) * HW + pix;
         if (f + 0 < F) o[0] = acc.x;
@@ -663,10 +670,9 @@ k_dv_render_bwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const flo
                 const float *__restrict__ cam2world, const float *__restrict__ W1, const float *__restrict__ b1,
                 const float *__restrict__ W2, const float *__restrict__ b2, int F, const float *__restrict__ g_novel,
                 const float *__restrict__ g_depth, const float *__restrict__ g_fg, float *__restrict__ gcl,
-                float *__restrict__ partials, int nvals)
+                float *__restrict__ partials, int nvals, const float *__restrict__ saved)
 {
     __shared__ float s_c[kDvWarps][4][kRenderMaxD];
-    __shared__ float s_gw[kDvWarps][4][kRenderMaxD + 1];
     __shared__ float s_red[kDvWarps][kRenderNf * 33 + 2 * kRenderNf + 1];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -692,49 +698,52 @@ k_dv_render_bwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const flo
         gdm = (__ldg(g_depth + (size_t)b * HW + pix) * P.voxel_size) * (float)R.depth_steps;   // backward of :903-904
         if (g_fg) gfg = __ldg(g_fg + (size_t)b * HW + pix);
     }
-    float *sc = s_c[wid][eg], *sgw = s_gw[wid][eg];
-
-    // ---- pass 1: front to back
-    float c = 0.0f;
+    float *sc = s_c[wid][eg];
     int nd = 0;                                                          // depth steps that matter for this ray
-    bool done = !valid;
-    for (int d0 = 0; d0 < P.D; d0 += 8) {
-        if (__all_sync(FULL, done)) break;
-        RayTaps mine;
-        render_taps(P, T, d0 + fq, pix, valid && !done, F, mine);
+
+    // ---- pass 1: front to back -- only when the forward did not leave its running sums (`saved`)
+    if (saved) {
+        const float *sv = saved + ((size_t)b * HW + (valid ? pix : 0)) * (P.D + 1);
+        nd = valid ? __float_as_int(__ldg(sv)) : 0;
+        for (int d = fq; d < nd; d += 8) sc[d] = __ldg(sv + 1 + d);
+    } else {
+        float c = 0.0f;
+        bool done = !valid;
+        for (int d0 = 0; d0 < P.D; d0 += 8) {
+            if (__all_sync(FULL, done)) break;
+            RayTaps mine;
+            render_taps(P, T, d0 + fq, pix, valid && !done, F, mine);
 #pragma unroll 1
-        for (int q = 0; q < 8; ++q) {
-            const int d = d0 + q;
-            if (d >= P.D) break;
-            const int sl = gbase | q;
-            const int keep = __shfl_sync(FULL, mine.keep, sl);
-            int off[8];
-            float wk[8];
+            for (int q = 0; q < 8; ++q) {
+                const int d = d0 + q;
+                if (d >= P.D) break;
+                const int sl = gbase | q;
+                const int keep = __shfl_sync(FULL, mine.keep, sl);
+                int off[8];
+                float wk[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { off[k] = __shfl_sync(FULL, mine.off[k], sl); wk[k] = __shfl_sync(FULL, mine.w[k], sl); }
-            float4 feat = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (keep && !done && f < F) {
+                for (int k = 0; k < 8; ++k) { off[k] = __shfl_sync(FULL, mine.off[k], sl); wk[k] = __shfl_sync(FULL, mine.w[k], sl); }
+                float4 feat = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (keep && !done && f < F) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(src + (off[k] + f)));
-                    feat.x = fmaf(v.x, wk[k], feat.x); feat.y = fmaf(v.y, wk[k], feat.y);
-                    feat.z = fmaf(v.z, wk[k], feat.z); feat.w = fmaf(v.w, wk[k], feat.w);
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(src + (off[k] + f)));
+                        feat.x = fmaf(v.x, wk[k], feat.x); feat.y = fmaf(v.y, wk[k], feat.y);
+                        feat.z = fmaf(v.z, wk[k], feat.z); feat.w = fmaf(v.w, wk[k], feat.w);
+                    }
                 }
-            }
-            const float dc = __shfl_sync(FULL, mine.dc, sl);
-            float a[kRenderNf];
-            const float occ = render_mlp(w, R, feat, dc, a);
-            // dL/dw_d = <g_novel, feat_d> + g_depth_map * depth_coord_d + g_fg      (:583,:888,:892)
-            const float dot = group8_sum(fmaf(gcol.w, feat.w, fmaf(gcol.z, feat.z, fmaf(gcol.y, feat.y, gcol.x * feat.x))));
-            if (!done) {
-                c += occ;
-                if (fq == 0) { sc[d] = c; sgw[d] = fmaf(gdm, dc, dot) + gfg; }
-                nd = d + 1;
-                if (c > 1.0f) done = true;
+                const float dc = __shfl_sync(FULL, mine.dc, sl);
+                float a[kRenderNf];
+                const float occ = render_mlp(w, R, feat, dc, a);
+                if (!done) {
+                    c += occ;
+                    if (fq == 0) sc[d] = c;
+                    nd = d + 1;
+                    if (c > 1.0f) done = true;
+                }
             }
         }
     }
-    if (fq == 0 && valid) sgw[nd] = 0.0f;                                // no weight behind the last step
     __syncwarp();
 
     // ---- pass 2: back to front
@@ -749,6 +758,7 @@ k_dv_render_bwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const flo
     ndmax = max(ndmax, __shfl_xor_sync(FULL, ndmax, 8));
     ndmax = max(ndmax, __shfl_xor_sync(FULL, ndmax, 16));
     float S = 0.0f;                                                      // suffix sum of dL/dc (F.cumsum backward)
+    float gw_next = 0.0f;                                                // dL/dw_{d+1} (0 behind the last step)
     for (int d0 = ((ndmax - 1) >> 3) << 3; d0 >= 0; d0 -= 8) {
         RayTaps mine;
         render_taps(P, T, d0 + fq, pix, valid && (d0 + fq) < nd, F, mine);
@@ -775,10 +785,14 @@ k_dv_render_bwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const flo
             const float dc = __shfl_sync(FULL, mine.dc, sl);
             float a[kRenderNf];
             const float occ = render_mlp(w, R, ft, dc, a);
+            // dL/dw_d = <g_novel, feat_d> + g_depth_map * depth_coord_d + g_fg      (:583,:888,:892)
+            const float dot = group8_sum(fmaf(gcol.w, ft.w, fmaf(gcol.z, ft.z, fmaf(gcol.y, ft.y, gcol.x * ft.x))));
             if (!active) continue;
+            const float gw = fmaf(gdm, dc, dot) + gfg;
             const float cd = sc[d], cp = d > 0 ? sc[d - 1] : 0.0f;
             const float wd = fminf(fmaxf(cd, 0.0f), 1.0f) - fminf(fmaxf(cp, 0.0f), 1.0f);
-            if (cd >= 0.0f && cd <= 1.0f) S += sgw[d] - sgw[d + 1];     // Clip backward (inclusive bounds), diff backward
+            if (cd >= 0.0f && cd <= 1.0f) S += gw - gw_next;            // Clip backward (inclusive bounds), diff backward
+            gw_next = gw;
             const float gs = S * occ * (1.0f - occ);                     // Sigmoid backward
             gb2 += gs;
             float gx0 = 0.0f, gx1 = 0.0f, gx2 = 0.0f, gx3 = 0.0f;
@@ -1060,6 +1074,12 @@ static RenderWs render_ws(const rgbd_dv_params *p, int B, int F)
     return w;
 }
 
+RGBD_API size_t rgbd_dv_render_saved_bytes(const rgbd_dv_params *p, int B)
+{
+    if (!dv_ok(p) || B <= 0) return 0;
+    return (size_t)B * p->W * p->H * (p->D + 1) * sizeof(float);
+}
+
 RGBD_API size_t rgbd_dv_render_workspace_bytes(const rgbd_dv_params *p, int B, int F)
 {
     if (!dv_ok(p) || B <= 0 || F <= 0) return 0;
@@ -1068,8 +1088,8 @@ RGBD_API size_t rgbd_dv_render_workspace_bytes(const rgbd_dv_params *p, int B, i
 
 RGBD_API int rgbd_dv_render_fwd(const rgbd_dv_params *p, const rgbd_dv_render_params *r, const float *grid,
                        const float *cam2world, const float *W1, const float *b1, const float *W2, const float *b2,
-                       int B, int F, float *novel, float *depth, float *fg, void *workspace, size_t workspace_bytes,
-                       void *stream)
+                       int B, int F, float *novel, float *depth, float *fg, float *saved, void *workspace,
+                       size_t workspace_bytes, void *stream)
 {
     if (!render_ok(p, r, B, F)) return RGBD_E_UNSUPPORTED;
     if (!grid || !cam2world || !W1 || !b1 || !W2 || !b2 || !novel || !depth) {
@@ -1086,7 +1106,8 @@ RGBD_API int rgbd_dv_render_fwd(const rgbd_dv_params *p, const rgbd_dv_render_pa
         k_dv_to_cl<<<dim3((G3 + 31) / 32, (F + 31) / 32, nb), dim3(32, 8), 0, st>>>(grid + (size_t)b0 * F * G3, cl, F, G3);
         k_dv_render_fwd<<<dim3(L.nblk, nb), 32 * kDvWarps, 0, st>>>(*p, *r, cl, cam2world + 16 * (size_t)b0, W1, b1, W2, b2, F,
                                                                   novel + (size_t)b0 * F * HW, depth + (size_t)b0 * HW,
-                                                                  fg ? fg + (size_t)b0 * HW : nullptr);
+                                                                  fg ? fg + (size_t)b0 * HW : nullptr,
+                                                                  saved ? saved + (size_t)b0 * HW * (p->D + 1) : nullptr);
         count_launch(2);
     }
     return check_launch("rgbd_dv_render_fwd");
@@ -1094,9 +1115,9 @@ RGBD_API int rgbd_dv_render_fwd(const rgbd_dv_params *p, const rgbd_dv_render_pa
 
 RGBD_API int rgbd_dv_render_bwd(const rgbd_dv_params *p, const rgbd_dv_render_params *r, const float *grid,
                        const float *cam2world, const float *W1, const float *b1, const float *W2, const float *b2,
-                       int B, int F, const float *g_novel, const float *g_depth, const float *g_fg, float *g_grid,
-                       float *g_W1, float *g_b1, float *g_W2, float *g_b2, void *workspace, size_t workspace_bytes,
-                       void *stream)
+                       int B, int F, const float *saved, const float *g_novel, const float *g_depth, const float *g_fg,
+                       float *g_grid, float *g_W1, float *g_b1, float *g_W2, float *g_b2, void *workspace,
+                       size_t workspace_bytes, void *stream)
 {
     if (!render_ok(p, r, B, F)) return RGBD_E_UNSUPPORTED;
     if (!grid || !cam2world || !W1 || !b1 || !W2 || !b2 || !g_novel || !g_depth || !g_grid || !g_W1 || !g_b1 || !g_W2 || !g_b2) {
@@ -1117,7 +1138,7 @@ RGBD_API int rgbd_dv_render_bwd(const rgbd_dv_params *p, const rgbd_dv_render_pa
         k_dv_render_bwd<<<dim3(L.nblk, nb), 32 * kDvWarps, 0, st>>>(
             *p, *r, cl, cam2world + 16 * (size_t)b0, W1, b1, W2, b2, F, g_novel + (size_t)b0 * F * HW,
             g_depth + (size_t)b0 * HW, g_fg ? g_fg + (size_t)b0 * HW : nullptr, gcl,
-            partials + (size_t)b0 * L.nblk * L.nvals, L.nvals);
+            partials + (size_t)b0 * L.nblk * L.nvals, L.nvals, saved ? saved + (size_t)b0 * HW * (p->D + 1) : nullptr);
         k_dv_from_cl<<<dim3((G3 + 31) / 32, (F + 31) / 32, nb), dim3(32, 8), 0, st>>>(gcl, g_grid + (size_t)b0 * F * G3, F, G3);
         count_launch(3);
     }

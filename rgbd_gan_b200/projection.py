@@ -153,10 +153,14 @@ class _RenderFn(torch.autograd.Function):
         depth = torch.empty((B, 1, params.H, params.W), dtype=torch.float32, device=dev)
         fg = torch.empty((B, 1, params.H, params.W), dtype=torch.float32, device=dev)
         ws = torch.empty(_lib.load().rgbd_dv_render_workspace_bytes(ctypes.byref(params), B, F), dtype=torch.uint8, device=dev)
+        need_grad = any(ctx.needs_input_grad[:5])
+        saved = torch.empty(_lib.load().rgbd_dv_render_saved_bytes(ctypes.byref(params), B) // 4, dtype=torch.float32,
+                            device=dev) if need_grad else None         # running sums of every ray, for backward
         _lib.call("rgbd_dv_render_fwd", ctypes.byref(params), ctypes.byref(rparams), _ptr(grid), _ptr(cam), _ptr(W1),
-                  _ptr(b1), _ptr(W2), _ptr(b2), B, F, _ptr(novel), _ptr(depth), _ptr(fg), _ptr(ws), ws.numel(), _stream())
+                  _ptr(b1), _ptr(W2), _ptr(b2), B, F, _ptr(novel), _ptr(depth), _ptr(fg),
+                  None if saved is None else _ptr(saved), _ptr(ws), ws.numel(), _stream())
         ctx.save_for_backward(grid, W1, b1, W2, b2, cam)
-        ctx.params, ctx.rparams, ctx.ws = params, rparams, ws
+        ctx.params, ctx.rparams, ctx.ws, ctx.saved = params, rparams, ws, saved
         return novel, depth, fg
 
     @staticmethod
@@ -170,7 +174,8 @@ class _RenderFn(torch.autograd.Function):
         g_grid = torch.empty_like(grid)
         gW1, gb1, gW2, gb2 = torch.empty_like(W1), torch.empty_like(b1), torch.empty_like(W2), torch.empty_like(b2)
         _lib.call("rgbd_dv_render_bwd", ctypes.byref(ctx.params), ctypes.byref(ctx.rparams), _ptr(grid), _ptr(cam),
-                  _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), B, F, _ptr(g_novel), _ptr(g_depth),
+                  _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), B, F, None if ctx.saved is None else _ptr(ctx.saved),
+                  _ptr(g_novel), _ptr(g_depth),
                   None if g_fg is None else _ptr(g_fg), _ptr(g_grid), _ptr(gW1), _ptr(gb1), _ptr(gW2), _ptr(gb2),
                   _ptr(ctx.ws), ctx.ws.numel(), _stream())
         return g_grid, gW1, gb1, gW2, gb2, None, None, None

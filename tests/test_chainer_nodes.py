@@ -157,16 +157,16 @@ class OracleBackedLib:
             W1, b1, W2, b2 = _view(a[4], (R.nf, F + 1)), _view(a[5], (R.nf,)), _view(a[6], (1, R.nf)), _view(a[7], (1,))
             args = (P0, grid, cam, W1, b1, W2, b2, R.threshold, R.inv_c1, R.inv_c2, R.depth_steps)
             if name == "rgbd_dv_render_fwd":
-                assert len(a) == 16
+                assert len(a) == 17 and a[13].value
                 novel, depth, fg = self.oracle.dv_render_fwd(*args)
                 _view(a[10], (B, F, HW))[...] = novel.reshape(B, F, HW)
                 _view(a[11], (B, HW))[...] = depth.reshape(B, HW)
                 _view(a[12], (B, HW))[...] = fg.reshape(B, HW)
             else:
-                assert len(a) == 21
-                g_fg = _view(a[12], (B, P.H, P.W))
-                outs = self.oracle.dv_render_bwd(*args, _view(a[10], (B, F, P.H, P.W)), _view(a[11], (B, P.H, P.W)), g_fg)
-                for ptr, o in zip(a[13:18], outs):
+                assert len(a) == 22 and a[10].value
+                g_fg = _view(a[13], (B, P.H, P.W))
+                outs = self.oracle.dv_render_bwd(*args, _view(a[11], (B, F, P.H, P.W)), _view(a[12], (B, P.H, P.W)), g_fg)
+                for ptr, o in zip(a[14:19], outs):
                     _view(ptr, o.shape)[...] = o
         else:
             raise AssertionError("unexpected C-ABI call " + name)

@@ -18,7 +18,7 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / max(float(np.abs(b).max()), 1e-30))
 
 
-def _call(P, R, grid, cam, W1, b1, W2, b2, g_novel=None, g_depth=None, g_fg=None):
+def _call(P, R, grid, cam, W1, b1, W2, b2, g_novel=None, g_depth=None, g_fg=None, use_saved=True):
     from gpu_util import DEV, dev, p, stream
     from rgbd_gan_b200 import _lib
     B, F = grid.shape[:2]
@@ -28,8 +28,10 @@ def _call(P, R, grid, cam, W1, b1, W2, b2, g_novel=None, g_depth=None, g_fg=None
     novel = torch.full((B, F, HW), float("nan"), device=DEV)
     depth = torch.full((B, HW), float("nan"), device=DEV)
     fg = torch.full((B, HW), float("nan"), device=DEV)
+    saved = torch.full((_lib.load().rgbd_dv_render_saved_bytes(ctypes.byref(P), B) // 4,), float("nan"), device=DEV) \
+        if use_saved else None
     _lib.call("rgbd_dv_render_fwd", ctypes.byref(P), ctypes.byref(R), *[p(t) for t in d], B, F, p(novel), p(depth), p(fg),
-              p(ws), ws.numel(), stream())
+              p(saved), p(ws), ws.numel(), stream())
     out = [novel.cpu().numpy(), depth.cpu().numpy(), fg.cpu().numpy()]
     if g_novel is None:
         return out
@@ -37,7 +39,7 @@ def _call(P, R, grid, cam, W1, b1, W2, b2, g_novel=None, g_depth=None, g_fg=None
     gW1, gb1 = torch.full(W1.shape, float("nan"), device=DEV), torch.full(b1.shape, float("nan"), device=DEV)
     gW2, gb2 = torch.full((W2.size,), float("nan"), device=DEV), torch.full((1,), float("nan"), device=DEV)
     ups = [dev(g_novel), dev(g_depth), None if g_fg is None else dev(g_fg)]     # keep the device copies alive
-    _lib.call("rgbd_dv_render_bwd", ctypes.byref(P), ctypes.byref(R), *[p(t) for t in d], B, F, p(ups[0]), p(ups[1]),
+    _lib.call("rgbd_dv_render_bwd", ctypes.byref(P), ctypes.byref(R), *[p(t) for t in d], B, F, p(saved), p(ups[0]), p(ups[1]),
               p(ups[2]), p(gg), p(gW1), p(gb1), p(gW2), p(gb2), p(ws), ws.numel(), stream())
     torch.cuda.synchronize()
     return out + [t.cpu().numpy() for t in (gg, gW1, gb1, gW2, gb2)]
@@ -52,13 +54,16 @@ def _params(G, img, D, voxel_size, near_plane, F, nf, threshold):
     return P, R
 
 
+@pytest.mark.parametrize("use_saved", [True, False])
 @pytest.mark.parametrize("name", RENDER_CASES)
-def test_render_against_reference_golden(name):
+def test_render_against_reference_golden(name, use_saved):
+    """use_saved: the backward reads the running sums the forward left (one reverse sweep); otherwise it repeats
+    the forward walk first -- same results"""
     g = load_golden(name)
     G, img, F, D = int(g["G"]), int(g["img"]), int(g["F"]), int(g["D"])
     P, R = _params(G, img, D, float(g["voxel_size"]), float(g["near_plane"]), F, int(g["nf"]), float(g["threshold"]))
     novel, depth, fg, gg, gW1, gb1, gW2, gb2 = _call(P, R, g["grid"], g["cam"], g["W1"], g["b1"], g["W2"], g["b2"],
-                                                      g["g_novel"], g["g_depth"], g["g_fg"])
+                                                      g["g_novel"], g["g_depth"], g["g_fg"], use_saved=use_saved)
     assert _rel(novel.reshape(g["novel"].shape), g["novel"]) <= 1e-5
     assert _rel(depth.reshape(g["depth"].shape), g["depth"]) <= 1e-5
     assert _rel(fg.reshape(g["fg"].shape), g["fg"]) <= 1e-5
@@ -129,7 +134,7 @@ def test_render_full_size_against_oracle_and_properties(G, B, oracle_mod):
         assert _rel(got, want) <= 2e-5
     # without g_fg == with zeros
     out2 = _call(P, R, grid, cam, W1, b1, W2, b2, g_novel, g_depth, None)
-    out3 = _call(P, R, grid, cam, W1, b1, W2, b2, g_novel, g_depth, np.zeros_like(g_fg))
+    out3 = _call(P, R, grid, cam, W1, b1, W2, b2, g_novel, g_depth, np.zeros_like(g_fg), use_saved=False)
     np.testing.assert_allclose(out2[4], out3[4], rtol=1e-6, atol=1e-9)
 
 
@@ -140,5 +145,5 @@ def test_render_rejects_unsupported_shapes():
     R.nf = 8
     x = torch.zeros(64, device=DEV)
     rc = _lib.load().rgbd_dv_render_fwd(ctypes.byref(P), ctypes.byref(R), p(x), p(x), p(x), p(x), p(x), p(x), 1, 32,
-                                        p(x), p(x), None, p(x), 0, stream())
+                                        p(x), p(x), None, None, p(x), 0, stream())
     assert rc == -4
