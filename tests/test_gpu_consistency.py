@@ -186,6 +186,28 @@ def test_pipeline_kernel_agrees_with_reference(name, lags, monkeypatch):
     assert status.value == 0
 
 
+@pytest.mark.parametrize("name", ["loss_s32_l2_feat", "loss_edge_c2"])
+@pytest.mark.parametrize("wide", ["1", "0"])
+def test_many_channel_kernels_agree_with_reference(name, wide, monkeypatch):
+    """C != 4 (the feature-space loss of updater.py:345-354): the warp-per-pixel kernels (default) and the simple
+    thread-per-pixel variant (RGBD_B200_WIDE=0) both reproduce the reference, incl. new_zp, masks and the two-pass path"""
+    monkeypatch.setenv("RGBD_B200_WIDE", wide)
+    g = load_golden(name)
+    o = case_options(g)
+    drv = _driver(g, o)
+    parts, gi, gr = drv.fwd_bwd(gy=o["gy"])
+    assert abs(parts[4] - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert_grad_close(gi, g["g_img"])
+    assert_grad_close(gr, g["g_img_rot"])
+    parts2, zp, masks = drv.fwd()
+    np.testing.assert_array_equal(zp, g["new_zp_cat"])
+    np.testing.assert_array_equal(masks[0].astype(bool), np.concatenate([g["not_out"], g["not_out_rot"]]))
+    np.testing.assert_allclose(parts2[:5], parts[:5], rtol=1e-6)
+    gi2, gr2 = drv.bwd(gy=1.0, gy_dev=o["gy"])
+    assert_grad_close(gi2, g["g_img"])
+    assert_grad_close(gr2, g["g_img_rot"])
+
+
 def test_growing_sizes_reuse():
     g = load_golden("loss_growing")
     from gpu_util import Consistency
