@@ -1060,11 +1060,24 @@ static bool render_ok(const rgbd_dv_params *p, const rgbd_dv_render_params *r, i
 
 struct RenderWs { size_t cl, gcl, partials, total; int Bs, nblk, nvals; };
 
+// samples per launch of the render kernels: a sample has only H*W rays (4096 = 1024 warps), so one sample cannot fill
+// the GPU; when the L2-sized chunk of the projection kernels is a single sample (G = 64: 33.5 MB per staged grid)
+// several samples are launched together even though their staged grids then exceed L2 (measured, r01_tuning.md)
+static int render_chunk_samples(const rgbd_dv_params *p, int B, int F)
+{
+    int n = (int)dv_chunk_samples(p, B, F);
+    const char *e = getenv("RGBD_B200_DV_RENDER_CHUNK");
+    const int want = (e && atoi(e) > 0) ? atoi(e) : 8;
+    if (n < want) n = want;
+    if (n > B) n = B;
+    return n;
+}
+
 static RenderWs render_ws(const rgbd_dv_params *p, int B, int F)
 {
     RenderWs w;
     const size_t per = (size_t)p->G * p->G * p->G * F * sizeof(float);
-    w.Bs = (int)dv_chunk_samples(p, B, F);
+    w.Bs = render_chunk_samples(p, B, F);
     w.nblk = (p->W * p->H + 4 * kDvWarps - 1) / (4 * kDvWarps);
     w.nvals = kRenderNf * (F + 1) + 2 * kRenderNf + 1;
     w.cl = 0;
