@@ -19,13 +19,14 @@ __device__ __forceinline__ Cam load_cam(const float *__restrict__ cam2world)
 }
 
 // voxel coordinates of frustum element l; returns the in-bounds flag (projection.py:64-96)
-__device__ __forceinline__ bool dv_coords(const rgbd_dv_params &P, const Cam &T, int l, float vc[3])
+// (d, tmp) = (l // (W*H), l - d*W*H) given directly
+__device__ __forceinline__ bool dv_coords_at(const rgbd_dv_params &P, const Cam &T, int d, int tmp, float vc[3])
 {
-    const int WH = P.W * P.H;
-    const int d = l / WH;                                             // :64
-    const int tmp = l - d * WH;                                       // :65-66
-    const float yrow = (float)((double)tmp / (double)P.W);            // :67 true division (fractional row, Q5)
-    const float xcol = (float)(tmp % P.W);                            // :68
+    // :67 true division (fractional row, Q5).  For a power-of-two width the float64 quotient is exactly tmp * 2^-k
+    // (tmp < 2^24), so one exact fp32 multiply replaces the double division
+    const bool pow2 = (P.W & (P.W - 1)) == 0 && P.W * P.H <= (1 << 24);
+    const float yrow = pow2 ? __fmul_rn((float)tmp, 1.0f / (float)P.W) : (float)((double)tmp / (double)P.W);
+    const float xcol = (float)(pow2 ? (tmp & (P.W - 1)) : (tmp % P.W));   // :68
     float zc = __fmul_rn((float)d, P.voxel_size);                     // :73
     zc = __fadd_rn(zc, P.near_plane);                                 // :74 (fp32, Q6)
     float xc = __fdiv_rn(__fsub_rn(xcol, P.cx), P.fx);                // :78
@@ -45,6 +46,13 @@ __device__ __forceinline__ bool dv_coords(const rgbd_dv_params &P, const Cam &T,
         keep = keep && (v >= 0.0f) && (v < Gf);                       // :92-96
     }
     return keep;
+}
+
+__device__ __forceinline__ bool dv_coords(const rgbd_dv_params &P, const Cam &T, int l, float vc[3])
+{
+    const int WH = P.W * P.H;
+    const int d = l / WH;                                             // :64
+    return dv_coords_at(P, T, d, l - d * WH, vc);                     // :65-66
 }
 
 struct Taps {
@@ -549,6 +557,42 @@ __device__ __forceinline__ float render_depth_coord(int d, int D)
     return (float)((double)(lo + d) / (double)D);
 }
 
+// forward-only variant: the four hidden pre-activations are reduced TRANSPOSED over the 8 lanes (2 + 1 + 1 shuffles
+// leave lane (b2 b1 b0) with the complete sum of unit j = 2*b2 + b1), the output layer then needs 2 more shuffles:
+// 6 instead of 12, and every lane evaluates one hidden unit instead of four
+struct RenderWm { float w1d, b1, w2; };       // the constants of "my" hidden unit
+__device__ __forceinline__ RenderWm render_my_unit(const RenderW &w, int fq)
+{
+    const int j = ((fq >> 2) & 1) * 2 + ((fq >> 1) & 1);
+    RenderWm m;
+    m.w1d = j == 0 ? w.w1d[0] : (j == 1 ? w.w1d[1] : (j == 2 ? w.w1d[2] : w.w1d[3]));
+    m.b1 = j == 0 ? w.b1[0] : (j == 1 ? w.b1[1] : (j == 2 ? w.b1[2] : w.b1[3]));
+    m.w2 = j == 0 ? w.w2[0] : (j == 1 ? w.w2[1] : (j == 2 ? w.w2[2] : w.w2[3]));
+    return m;
+}
+__device__ __forceinline__ float render_mlp_fwd(const RenderW &w, const RenderWm &m, const rgbd_dv_render_params &R,
+                                                float4 feat, float dc, int fq)
+{
+    const unsigned FULL = 0xffffffffu;
+    const float x0 = R.inv_c1 * feat.x, x1 = R.inv_c1 * feat.y, x2 = R.inv_c1 * feat.z, x3 = R.inv_c1 * feat.w;
+    float p[kRenderNf];
+#pragma unroll
+    for (int j = 0; j < kRenderNf; ++j)
+        p[j] = fmaf(w.w1q[j][3], x3, fmaf(w.w1q[j][2], x2, fmaf(w.w1q[j][1], x1, w.w1q[j][0] * x0)));
+    const bool b2 = fq & 4, b1 = fq & 2;
+    const float r0 = __shfl_xor_sync(FULL, b2 ? p[0] : p[2], 4), r1 = __shfl_xor_sync(FULL, b2 ? p[1] : p[3], 4);
+    const float q0 = (b2 ? p[2] : p[0]) + r0, q1 = (b2 ? p[3] : p[1]) + r1;
+    float t = (b1 ? q1 : q0) + __shfl_xor_sync(FULL, b1 ? q0 : q1, 2);
+    t += __shfl_xor_sync(FULL, t, 1);
+    const float aj = (t + m.w1d * (R.inv_c1 * dc)) + m.b1;
+    const float h = aj < 0.0f ? 0.2f * aj : aj;
+    float s = m.w2 * (R.inv_c2 * h);
+    s += __shfl_xor_sync(FULL, s, 2);
+    s += __shfl_xor_sync(FULL, s, 4);
+    s = (s + w.b2) - R.threshold;
+    return tanhf(s * 0.5f) * 0.5f + 0.5f;
+}
+
 struct RayTaps { int off[8]; float w[8]; int keep; float dc; };
 
 // taps of frustum element (d, row, col) for the lane that owns depth slot `d`; folded corner weights
@@ -556,7 +600,7 @@ __device__ __forceinline__ void render_taps(const rgbd_dv_params &P, const Cam &
                                             RayTaps &t)
 {
     float vc[3] = {0.f, 0.f, 0.f};
-    const bool keep = valid && d < P.D && dv_coords(P, T, d * (P.W * P.H) + pix, vc);
+    const bool keep = valid && d < P.D && dv_coords_at(P, T, d, pix, vc);
     t.keep = keep ? 1 : 0;
     t.dc = render_depth_coord(d, P.D);          // (a double division: once per chunk and lane, then shuffled)
     if (keep) {
@@ -592,6 +636,7 @@ k_dv_render_fwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const flo
     const bool valid = pix < HW;
     const Cam T = load_cam(cam2world + 16 * b);
     const RenderW w = render_load_w(W1, b1, W2, b2, F, fq);
+    const RenderWm wm = render_my_unit(w, fq);
     const size_t G3 = (size_t)P.G * P.G * P.G;
     const float *__restrict__ src = cl + (size_t)b * G3 * F;
     const int f = 4 * fq;
@@ -628,8 +673,7 @@ k_dv_render_fwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const flo
                 }
             }
             const float dc = __shfl_sync(FULL, mine.dc, sl);
-            float a[kRenderNf];
-            const float occ = render_mlp(w, R, feat, dc, a);            // (shuffles: executed by every lane)
+            const float occ = render_mlp_fwd(w, wm, R, feat, dc, fq);   // (shuffles: executed by every lane)
             if (!done) {
                 c += occ;                                               // F.cumsum
                 const float clip = fminf(fmaxf(c, 0.0f), 1.0f);         // F.clip(., 0, 1)
