@@ -618,7 +618,7 @@ __device__ __forceinline__ void render_taps(const rgbd_dv_params &P, const Cam &
 }
 
 #ifndef RGBD_RENDER_MINBLK
-#define RGBD_RENDER_MINBLK 2
+#define RGBD_RENDER_MINBLK 3
 #endif
 // one warp = 4 rays x 8 feature quads; block = 8 warps = 32 consecutive pixels
 __global__ void __launch_bounds__(32 * kDvWarps, RGBD_RENDER_MINBLK)
@@ -709,7 +709,10 @@ k_dv_render_fwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const flo
 // with the suffix sum of dL/dc (backward of F.cumsum), re-gathers the features, back-propagates the occlusion
 // MLP (weight gradients accumulate in registers, reduced once per block) and scatters dL/dfeature into the
 // channels-last grid gradient with 16-byte REDs (the lift).  Depths behind the first c_d > 1 carry no gradient.
-__global__ void __launch_bounds__(32 * kDvWarps)
+#ifndef RGBD_RENDER_BWD_MINBLK
+#define RGBD_RENDER_BWD_MINBLK 2
+#endif
+__global__ void __launch_bounds__(32 * kDvWarps, RGBD_RENDER_BWD_MINBLK)
 k_dv_render_bwd(const rgbd_dv_params P, const rgbd_dv_render_params R, const float *__restrict__ cl,
                 const float *__restrict__ cam2world, const float *__restrict__ W1, const float *__restrict__ b1,
                 const float *__restrict__ W2, const float *__restrict__ b2, int F, const float *__restrict__ g_novel,
