@@ -720,11 +720,23 @@ def main():
     if a.impl == "reference":
         run_reference(a)
         return
+    # stdout carries exactly ONE line (the JSON record): while the benchmark runs, file descriptor 1 points at stderr,
+    # so banners that libraries write to stdout (e.g. "NCCL version ..." at communicator creation) end up there
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(record):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(record), flush=True)
+        os.dup2(2, 1)
+
     line, ctx_ = run_ours(a)
     if ctx_["world"] > 1:
         import torch.distributed as dist
         if line is not None:
-            print(json.dumps(line), flush=True)
+            emit(line)
         dist.barrier()
         dist.destroy_process_group()
         return
@@ -741,7 +753,7 @@ def main():
         line["feature_consistency_c257"] = feature_consistency_bench(a, ctx_)
     if not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg(a)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == "__main__":
