@@ -104,6 +104,13 @@ RGBD_API size_t rgbd_consistency_workspace_bytes(int B, int C, int H, int W);
  * raises a sticky flag instead of hanging the GPU.  Synchronises `stream`; *status_host = 0 ok, 1 timed out. */
 RGBD_API int rgbd_consistency_status(const void *workspace, void *stream, int *status_host);
 
+/* Test aid (no GPU needed): the ticket order of one launch of the pipeline kernel for a chunk of Bc pairs of H x W
+ * images: tickets[3t..3t+2] = (role, pair, tile) with role 0 none, 1 stage-in, 2 main, 3 stage-out, 4 loss finalize;
+ * *total_out = number of tickets.  tests/test_host_logic.py checks that every tile appears once and that every
+ * ticket depends only on tickets with smaller numbers (the property that makes the pipeline deadlock-free).      */
+RGBD_API int rgbd_debug_mega_schedule(int Bc, int H, int W, int grad, int fold, int lag_main, int lag_so,
+                                      int *tickets, int max_tickets, int *total_out);
+
 /* Forward only.  loss_parts (device, 8 floats): [0..3] = the four means of :141-144 restricted
  * to these B pairs, in the order {rgb, rgb_rot, depth, depth_rot}; [4] = the loss combined as
  * :141-144 does, (p0+p1) + (p2*lambda + p3*lambda), valid as is when the batch is not sharded

@@ -133,3 +133,43 @@ def test_dv_params_follow_generator_constants():
     assert P.voxel_size == np.float32(vs) and P.near_plane == np.float32(np.sqrt(3) / 4)
     with pytest.raises(ValueError):
         ProjectionHelper(intr, intr, [64, 64], [64, 64], 0., 1., [32, 32, 16], vs, 0.4, 56, verbose=False)
+
+
+@pytest.mark.parametrize("Bc,S,grad,fold,lags", [(1, 16, 1, 1, (1, 1)), (3, 32, 1, 1, (2, 3)), (5, 128, 1, 1, (2, 3)),
+                                                  (4, 64, 0, 1, (2, 3)), (4, 64, 1, 0, (1, 4)), (2, 128, 1, 1, (40, 40)),
+                                                  (7, 24, 1, 1, (3, 1))])
+def test_pipeline_ticket_schedule_is_complete_and_ordered(Bc, S, grad, fold, lags):
+    """the ticket order of the opt-in single-launch pipeline kernel (rgbd_debug_mega_schedule, host code only):
+    every stage-in / main / stage-out tile of every pair appears exactly once, there is one finalize ticket iff the
+    loss is folded in, and every ticket depends only on tickets with SMALLER numbers -- main(p) on all stage-in(p),
+    stage-out(p) on all main(p), finalize on all main -- which is what makes the in-order hand-out deadlock-free"""
+    import ctypes
+    from rgbd_gan_b200 import _lib
+    lib = _lib.load()
+    cap = 1 << 20
+    buf = (ctypes.c_int * (3 * cap))()
+    total = ctypes.c_int(0)
+    rc = lib.rgbd_debug_mega_schedule(Bc, S, S, grad, fold, lags[0], lags[1], buf, cap, ctypes.byref(total))
+    assert rc == 0 and 0 < total.value <= cap
+    t = np.ctypeslib.as_array(buf)[:3 * total.value].reshape(-1, 3)
+    HW = S * S
+    TS, TM = -(-HW // 1024), -(-HW // 512)
+    seen = {}
+    for n, (role, pair, idx) in enumerate(t):
+        if role == 0:
+            continue                                          # padding ticket (tile index beyond the image)
+        assert (role, pair, idx) not in seen
+        seen[(role, pair, idx)] = n
+    for p in range(Bc):
+        si = [seen[(1, p, i)] for i in range(2 * TS)]
+        mn = [seen[(2, p, i)] for i in range(2 * TM)]
+        assert max(si) < min(mn)
+        if grad:
+            so = [seen[(3, p, i)] for i in range(2 * TS)]
+            assert max(mn) < min(so)
+    n_fin = sum(1 for k in seen if k[0] == 4)
+    assert n_fin == (1 if fold else 0)
+    if fold:
+        assert all(v < seen[(4, 0, 0)] for k, v in seen.items() if k[0] == 2)
+    assert len(seen) == Bc * (2 * TS * (2 if grad else 1) + 2 * TM) + n_fin
+    assert lib.rgbd_debug_mega_schedule(Bc, S, S, grad, fold, 0, 1, buf, cap, ctypes.byref(total)) == -1   # lag 0 is refused
