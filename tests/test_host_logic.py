@@ -173,3 +173,25 @@ def test_pipeline_ticket_schedule_is_complete_and_ordered(Bc, S, grad, fold, lag
         assert all(v < seen[(4, 0, 0)] for k, v in seen.items() if k[0] == 2)
     assert len(seen) == Bc * (2 * TS * (2 if grad else 1) + 2 * TM) + n_fin
     assert lib.rgbd_debug_mega_schedule(Bc, S, S, grad, fold, 0, 1, buf, cap, ctypes.byref(total)) == -1   # lag 0 is refused
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU stand-in of the reference's path, runnable without a GPU): exactly one JSON
+    line on stdout with the keys the driver's contract names"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
