@@ -13,7 +13,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librgbdgan_b200.so")
 SOURCES = ["api.cu", "consistency.cu", "deepvoxels.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"),
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "sweep.cuh"),
            os.path.join(os.path.dirname(_HERE), "include", "rgbdgan_b200.h")]
 
 # No -use_fast_math: IEEE division/sqrt and no flush-to-zero are part of the parity contract.
