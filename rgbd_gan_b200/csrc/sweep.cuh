@@ -158,7 +158,7 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 // shared-memory layout: planes [2 images][4 channels][kSwNR rows][W] floats, then the barriers
 //   full[kSwNB], empty[kSwNB] : TMA ring;  reds[4] : compute -> retire ("REDs of step t are performed");
 //   zero[1 + 4] : retire -> compute ("the ring starts zeroed", "iteration t has written back and re-zeroed its block")
-template <int W, bool L1, bool LOSS, bool GRAD, bool RING>
+template <int W, bool L1, bool LOSS, bool GRAD, bool RING, bool HINGE>
 __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const SweepArgs a)
 {
     extern __shared__ __align__(128) unsigned char sw_smem[];
@@ -217,25 +217,25 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
     } else if (warp < kSwComputeWarps) {
         // ------------------------------------------------------------------ compute: warp = (row of block, direction)
         const int ri = warp & (kSwR - 1), dir = warp / kSwR;
-        const float *oth_gl = dir ? a.img : a.img_rot;
         const uint32_t sown_sa = smem_u32(sring + (dir ? img_stride : 0));
         const uint32_t soth_sa = smem_u32(sring + (dir ? 0 : img_stride));
-        float4 *ring_own = RING ? a.ring + ((size_t)cta * 2 + dir) * kSwRingRows * W : nullptr;
-        float4 *ring_oth = RING ? a.ring + ((size_t)cta * 2 + (1 - dir)) * kSwRingRows * W : nullptr;
-        SweepRec *ovf = a.ovf + (size_t)cta * a.ovf_cap;
+        // gradient accumulator: the CTA's ring [2][kSwRingRows][W] (debug variant: the global [2][B][HW] buffer)
+        float4 *const gbase = RING ? a.ring + (size_t)cta * 2 * kSwRingRows * W : a.gz;
         const float Hm1 = a.Hm1f;
         constexpr float Wm1 = (float)(W - 1);
-        const bool hinge = !isnan(a.hinge_min);
         const int Gs = LBs * kSwR, Gn = nsteps * kSwR;        // owned linear rows [Gs, Gs + Gn)
         const float xlane = (float)lane;
         float s_rgb = 0.0f, s_d = 0.0f, s_h = 0.0f;
         float4 pA = make_float4(0.f, 0.f, 0.f, 0.f), pB = pA, pC = pA;
-        int cur_pair = -1, q_waited = -1;
+        int cur_pair = -1, q_waited = -1, wait_slot = 0, wait_par = 0;
+        int own_slot = (LBs - Lfirst) % kSwNB;                               // ring slot of the own block
+        int win_slot = (LBs - kSwReach - Lfirst + kSwNB) % kSwNB;            // ring slot of the window's first block
 
+        int p = LBs / a.bpp, j = LBs - p * a.bpp - 1;          // pair and block-in-pair of the step (advanced below)
 #pragma unroll 1
         for (int t = 0; t < nsteps; ++t) {
             const int LB = LBs + t;
-            const int p = LB / a.bpp, j = LB - p * a.bpp;
+            if (++j == a.bpp) { j = 0; ++p; }
             if (p != cur_pair) {
                 // rows of K R K^-1: (pA.x pA.y pA.z) (pA.w pB.x pB.y) (pB.z pB.w pC.x); subtracted vector (pC.y pC.z pC.w)
                 const float *Ms = (dir ? a.Mi : a.M) + 9 * (size_t)p, *cs = (dir ? a.ci : a.c) + 3 * (size_t)p;
@@ -249,15 +249,16 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
                 const int q_need = top - Lfirst;
                 while (q_waited < q_need) {
                     ++q_waited;
-                    mbar_wait(bar_full + 8 * (q_waited % kSwNB), (uint32_t)((q_waited / kSwNB) & 1));
+                    mbar_wait(bar_full + 8 * wait_slot, (uint32_t)wait_par);
+                    if (++wait_slot == kSwNB) { wait_slot = 0; wait_par ^= 1; }
                 }
             }
             // ---- warp-uniform values of this step
             const int i = j * kSwR + ri;                                  // own row
             const float y = (float)i;
-            const int own_srow = ((LB - Lfirst) % kSwNB) * kSwR + ri;
+            const int own_srow = own_slot * kSwR + ri;
             const int qw = LB - kSwReach - Lfirst;                        // load index of the window's first block (may be < 0)
-            const int ws = ((qw + kSwNB) % kSwNB) * kSwR;                 // its ring row
+            const int ws = win_slot * kSwR;                               // its ring row
             const int wlo = (j - kSwReach) * kSwR;                        // first row of the window
             const int Grow0 = (LB - j) * kSwR;                            // linear row of this pair's row 0
             // rows of the other image whose scatter goes to the ring: inside the window AND owned by this CTA
@@ -266,10 +267,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
             rhi = rhi < wlo + kSwWin ? rhi : wlo + kSwWin;
             const unsigned rn = rhi > rlo ? (unsigned)(rhi - rlo) : 0u;
             const uint32_t own_sa = sown_sa + (uint32_t)(own_srow * W + lane) * 4u;
-            float4 *gown_row = (RING ? ring_own + (size_t)((Grow0 + i) & (kSwRingRows - 1)) * W
-                                     : a.gz + ((size_t)(dir * a.B + p) * HW + (size_t)i * W)) + lane;
-            float4 *goth = RING ? ring_oth : a.gz + (size_t)((1 - dir) * a.B + p) * HW;
-            const float *oth_pl = oth_gl + (size_t)p * 4 * HW;
+            const unsigned gown_off = (RING ? (unsigned)(dir * kSwRingRows + ((Grow0 + i) & (kSwRingRows - 1))) * W
+                                            : (unsigned)(dir * a.B + p) * HW + (unsigned)i * W) + lane;
+            const unsigned goth_off = RING ? (unsigned)((1 - dir) * kSwRingRows) * W : (unsigned)((1 - dir) * a.B + p) * HW;
 
 #pragma unroll 1
             for (int c0 = 0; c0 < W; c0 += 64) {
@@ -311,26 +311,25 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
                     const bool inw = (unsigned)rel < (unsigned)kSwWin;
                     int sr = ws + rel;
                     sr = sr >= kSwNR ? sr - kSwNR : sr;
-                    tapv[k] = soth_sa + (uint32_t)(sr * W + v0) * 4u;
                     mv[k] = m; okv[k] = m && inw; u0v[k] = u0; v0v[k] = v0;
+                    // taps that are masked or outside the window read the own pixel instead (always resident; the values
+                    // are never used: masked pixels are excluded below, far taps are re-read through L2)
+                    tapv[k] = okv[k] ? soth_sa + (uint32_t)(sr * W + v0) * 4u : own_sa + (uint32_t)(c0 + 32 * k) * 4u;
                     any_far = any_far || (m && !inw);
                 }
                 // ---- phase 3: the 2-tap gathers; both row taps read row u0 (:219)
                 float4 Av[2], Bv[2];
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    Av[k] = make_float4(0.f, 0.f, 0.f, 0.f); Bv[k] = Av[k];
-                    if (okv[k]) {
-                        const uint32_t tp = tapv[k];
-                        Av[k] = make_float4(lds_f32(tp), lds_f32(tp + PSB), lds_f32(tp + 2 * PSB), lds_f32(tp + 3 * PSB));
-                        Bv[k] = make_float4(lds_f32(tp + 4), lds_f32(tp + PSB + 4), lds_f32(tp + 2 * PSB + 4), lds_f32(tp + 3 * PSB + 4));
-                    }
+                    const uint32_t tp = tapv[k];
+                    Av[k] = make_float4(lds_f32(tp), lds_f32(tp + PSB), lds_f32(tp + 2 * PSB), lds_f32(tp + 3 * PSB));
+                    Bv[k] = make_float4(lds_f32(tp + 4), lds_f32(tp + PSB + 4), lds_f32(tp + 2 * PSB + 4), lds_f32(tp + 3 * PSB + 4));
                 }
                 if (__any_sync(0xffffffffu, any_far)) {                   // outside the window: through L2, exact but slow
 #pragma unroll
                     for (int k = 0; k < 2; ++k)
                         if (mv[k] && !okv[k]) {
-                            const float *tp = oth_pl + (size_t)u0v[k] * W + v0v[k];
+                            const float *tp = (dir ? a.img : a.img_rot) + (size_t)p * 4 * HW + (size_t)u0v[k] * W + v0v[k];
                             Av[k] = make_float4(__ldg(tp), __ldg(tp + HW), __ldg(tp + 2 * (size_t)HW), __ldg(tp + 3 * (size_t)HW));
                             Bv[k] = make_float4(__ldg(tp + 1), __ldg(tp + HW + 1), __ldg(tp + 2 * (size_t)HW + 1),
                                                 __ldg(tp + 3 * (size_t)HW + 1));
@@ -358,14 +357,14 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
                     const float w1 = __fmul_rn(wav[k], wcv[k]), w2 = __fmul_rn(wbv[k], wcv[k]),
                                 w3 = __fmul_rn(wav[k], wdv[k]), w4 = __fmul_rn(wbv[k], wdv[k]);
 #define RGBD_BLEND(ch) __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w1, A.ch), __fmul_rn(w2, A.ch)), __fmul_rn(w3, B4.ch)), __fmul_rn(w4, B4.ch))
-                    // sampled depth in the reference's exact order (it decides the occlusion mask); masked pixels have
-                    // A = B = 0 and are excluded through mv[] below
+                    // sampled depth in the reference's exact order (it decides the occlusion mask); masked pixels carry
+                    // arbitrary finite values and are excluded through mv[] below
                     const float wdp = RGBD_BLEND(w);
                     const bool o = a.occ ? (wdp > q2) : true;                         // :114 strict >
                     const bool sd = (ow.w < a.max_depth) && (ow.w > a.min_depth);     // :121-135
                     float gzo = 0.0f;                                                 // own-pixel depth gradient
                     bool own_red = false;
-                    if (hinge) {                                                      // updater.py:357-359
+                    if (HINGE) {                                                      // updater.py:357-359
                         const float h = fmaxf(a.hinge_min - ow.w, 0.0f);
                         if (LOSS) s_h += h * h;
                         if (GRAD && h > 0.0f) { gzo = a.hinge_coef * h; own_red = true; }
@@ -392,7 +391,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
                             const float e3 = sign_coeff(NORM, a.k_d, d3);
                             const int u0 = u0v[k], v0 = v0v[k];
                             if (!RING || (unsigned)(u0 - rlo) < rn) {                 // scatter-add (GetItem backward)
-                                float4 *gt = goth + (RING ? ((Grow0 + u0) & (kSwRingRows - 1)) * W + v0 : u0 * W + v0);
+                                float4 *gt = gbase + (goth_off + (RING ? ((Grow0 + u0) & (kSwRingRows - 1)) * W + v0 : u0 * W + v0));
                                 red_add_v4(gt, e0 * wA, e1 * wA, e2 * wA, e3 * wA);
                                 red_add_v4(gt + 1, e0 * wB, e1 * wB, e2 * wB, e3 * wB);
                             } else {                                                  // not this CTA's row (or out of window)
@@ -401,7 +400,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
                                 r.img = (1 - dir) * a.B + p; r.pix = u0 * W + v0; r.pad0 = r.pad1 = 0;
                                 r.ta = make_float4(e0 * wA, e1 * wA, e2 * wA, e3 * wA);
                                 r.tb = make_float4(e0 * wB, e1 * wB, e2 * wB, e3 * wB);
-                                ovf[slot] = r;
+                                a.ovf[(size_t)cta * a.ovf_cap + slot] = r;
                             }
                             const float GA = ((e0 * A.x + e1 * A.y) + e2 * A.z) + e3 * A.w;
                             const float GB = ((e0 * B4.x + e1 * B4.y) + e2 * B4.z) + e3 * B4.w;
@@ -417,15 +416,17 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
                             own_red = true;
                         }
                     }
-                    if (GRAD && own_red) red_add_v4(gown_row + (c0 + 32 * k), -e0, -e1, -e2, gzo);
+                    if (GRAD && own_red) red_add_v4(gbase + (gown_off + c0 + 32 * k), -e0, -e1, -e2, gzo);
 #undef RGBD_BLEND
                 }
             }
             // this step no longer needs the oldest block of the window
             if (qw >= 0) {
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8 * (qw % kSwNB));
+                if (lane == 0) mbar_arrive(bar_empty + 8 * win_slot);
             }
+            own_slot = own_slot + 1 == kSwNB ? 0 : own_slot + 1;
+            win_slot = win_slot + 1 == kSwNB ? 0 : win_slot + 1;
         }
         if (GRAD && RING && nsteps > 0) {
             fence_cta();
@@ -489,8 +490,9 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
 #pragma unroll
                         for (int k = 0; k < W / 32; ++k) {
                             st_cg_zero_v4(src + 32 * k);
-                            dst[32 * k] = v[n][k].x * scale; dst[HW + 32 * k] = v[n][k].y * scale;
-                            dst[2 * (size_t)HW + 32 * k] = v[n][k].z * scale; dst[3 * (size_t)HW + 32 * k] = v[n][k].w * scale;
+                            // written once, read by the caller's next kernels: streaming stores keep L2 for the ring
+                            __stcs(dst + 32 * k, v[n][k].x * scale); __stcs(dst + HW + 32 * k, v[n][k].y * scale);
+                            __stcs(dst + 2 * (size_t)HW + 32 * k, v[n][k].z * scale); __stcs(dst + 3 * (size_t)HW + 32 * k, v[n][k].w * scale);
                         }
                     }
                 }
@@ -518,20 +520,22 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
 
 // Adds the out-of-ring scatter contributions to the finished gradient planes (scalar atomics; a few percent of the
 // taps at chunk boundaries, everything outside the window for pathological inputs); the last block finishes the loss.
+constexpr int kSwFixSplit = 4;                           // fix-up blocks per list
 __global__ void __launch_bounds__(kThreads)
 k_sweep_fixup(const SweepArgs a, int nlists, const FinalizeArgs fin)
 {
     pdl_launch_dependents();
     pdl_wait();
-    if ((int)blockIdx.x == nlists) {
+    if ((int)blockIdx.x == nlists * kSwFixSplit) {
         if (fin.partials) loss_finalize_block(fin);
         return;
     }
     float scale = a.scale;
     if (a.scale_dev) scale *= __ldg(a.scale_dev);
-    const int n = a.ovf_count[blockIdx.x];
-    const SweepRec *recs = a.ovf + (size_t)blockIdx.x * a.ovf_cap;
-    for (int k = threadIdx.x; k < n; k += kThreads) {
+    const int list = blockIdx.x / kSwFixSplit, part = blockIdx.x % kSwFixSplit;
+    const int n = a.ovf_count[list];
+    const SweepRec *recs = a.ovf + (size_t)list * a.ovf_cap;
+    for (int k = part * kThreads + threadIdx.x; k < n; k += kSwFixSplit * kThreads) {
         const SweepRec r = recs[k];
         const int sel = r.img >= a.B ? 1 : 0, b = r.img - sel * a.B;
         float *g = (sel ? a.g_img_rot : a.g_img) + (size_t)b * 4 * a.HW + r.pix;
