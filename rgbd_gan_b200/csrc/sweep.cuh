@@ -9,7 +9,7 @@
 //   * All rows of all pairs form one linear sequence of BLOCKS of kSwR rows.  CTA i (one per SM, persistent) owns a
 //     contiguous range of blocks [LBs, LBe) -- perfectly balanced for every batch size -- and sweeps it top to bottom,
 //     both warp directions in lock step.
-//   * A producer thread streams the rows of BOTH images of the current pair straight from the caller's NCHW planes
+//   * One thread (of the retire warps) streams the rows of BOTH images of the current pair straight from the caller's NCHW planes
 //     into a shared-memory ring with cp.async.bulk (TMA, SASS UBLKCP) + mbarrier full / empty pairs: each row is
 //     fetched once and serves as "own pixels" for one direction and as gather window for the other.  The window is
 //     the own block +- kSwReach blocks (own row -16 .. +23 rows at kSwR = 8); the 2-tap gathers are LDS.
@@ -36,8 +36,8 @@ constexpr int kSwNR = kSwR * kSwNB;                      // ... rows per image
 constexpr int kSwReach = 2;                              // gather / scatter window: own block +- 2 blocks
 constexpr int kSwWin = (2 * kSwReach + 1) * kSwR;        // window rows
 constexpr int kSwComputeWarps = 2 * kSwR;                // one warp per (row of the block, direction)
-constexpr int kSwRetireWarps = 3;                        // 16 + 1 + 3 = 20 warps: 5 per scheduler, 96 registers each
-constexpr int kSwThreads = (kSwComputeWarps + 1 + kSwRetireWarps) * 32;
+constexpr int kSwRetireWarps = 4;                        // 16 + 4 = 20 warps: 5 per scheduler, 96 registers each
+constexpr int kSwThreads = (kSwComputeWarps + kSwRetireWarps) * 32;
 constexpr int kSwRingRows = 64;                          // global gradient ring: rows per image per CTA (power of two)
 constexpr int kSwBarBytes = 512;                        // barriers + reduction scratch behind the planes
 
@@ -156,7 +156,8 @@ __device__ __forceinline__ float lds_f32(uint32_t addr)
 }
 
 // shared-memory layout: planes [2 images][4 channels][kSwNR rows][W] floats, then the barriers
-//   full[kSwNB], empty[kSwNB] : TMA ring;  reds[4] : compute -> retire ("REDs of step t are performed");
+//   full[kSwNB] : TMA completion;  done[4] : compute -> retire ("step t is finished": its window rows were read, its REDs
+//   issued -- frees the oldest window block for the next TMA load and the oldest ring block for write-back);
 //   zero[1 + 4] : retire -> compute ("the ring starts zeroed", "iteration t has written back and re-zeroed its block")
 template <int W, bool L1, bool LOSS, bool GRAD, bool RING, bool HINGE>
 __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const SweepArgs a)
@@ -168,7 +169,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
     constexpr int img_stride = 4 * plane_stride;
     constexpr uint32_t PSB = plane_stride * sizeof(float);   // plane stride in bytes
     const uint32_t bars = smem_u32(sw_smem + (size_t)2 * img_stride * sizeof(float));
-    const uint32_t bar_full = bars, bar_empty = bars + 8 * kSwNB, bar_reds = bars + 16 * kSwNB, bar_zero = bar_reds + 32;
+    const uint32_t bar_full = bars, bar_done = bars + 16 * kSwNB, bar_zero = bar_done + 32;
     float *sred = reinterpret_cast<float *>(sw_smem + (size_t)2 * img_stride * sizeof(float) + 16 * kSwNB + 80);   // [3][16]
     int *scount = reinterpret_cast<int *>(sred + 3 * kSwComputeWarps);
 
@@ -181,8 +182,8 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
     const int nsteps = LBe - LBs;
 
     if (threadIdx.x == 0) {
-        for (int k = 0; k < kSwNB; ++k) { mbar_init(bar_full + 8 * k, 1); mbar_init(bar_empty + 8 * k, kSwComputeWarps); }
-        for (int k = 0; k < 4; ++k) mbar_init(bar_reds + 8 * k, kSwComputeWarps);
+        for (int k = 0; k < kSwNB; ++k) mbar_init(bar_full + 8 * k, 1);
+        for (int k = 0; k < 4; ++k) mbar_init(bar_done + 8 * k, kSwComputeWarps);
         for (int k = 0; k < 5; ++k) mbar_init(bar_zero + 8 * k, kSwRetireWarps);      // [0]: initial zero, [1..4]: retire iterations
         *scount = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -191,30 +192,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
     pdl_launch_dependents();
     pdl_wait();                       // inputs, ring and lists of the previous kernels on the stream are complete
 
-    if (warp == kSwComputeWarps) {
-        // ------------------------------------------------------------------ producer: one thread drives the TMA
-        if (lane == 0) {
-            uint64_t policy;
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-            constexpr uint32_t row_bytes = (uint32_t)(kSwR * W * sizeof(float));      // one plane of one block
-            const int nq = Llast - Lfirst + 1;
-            for (int q = 0; q < nq; ++q) {
-                const int slot = q % kSwNB;
-                if (q >= kSwNB) mbar_wait_relaxed(bar_empty + 8 * slot, (uint32_t)((q / kSwNB - 1) & 1));
-                const int L = Lfirst + q;
-                const int p = L / a.bpp, j = L - p * a.bpp;
-                mbar_expect_tx(bar_full + 8 * slot, 8 * row_bytes);
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const float *src = (s ? a.img_rot : a.img) + (size_t)p * 4 * HW + (size_t)j * kSwR * W;
-                    const uint32_t dst = smem_u32(sring + (size_t)s * img_stride + (size_t)slot * kSwR * W);
-#pragma unroll
-                    for (int ch = 0; ch < 4; ++ch)
-                        bulk_g2s(dst + ch * PSB, src + (size_t)ch * HW, row_bytes, bar_full + 8 * slot, policy);
-                }
-            }
-        }
-    } else if (warp < kSwComputeWarps) {
+    if (warp < kSwComputeWarps) {
         // ------------------------------------------------------------------ compute: warp = (row of block, direction)
         const int ri = warp & (kSwR - 1), dir = warp / kSwR;
         const uint32_t sown_sa = smem_u32(sring + (dir ? img_stride : 0));
@@ -257,7 +235,6 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
             const int i = j * kSwR + ri;                                  // own row
             const float y = (float)i;
             const int own_srow = own_slot * kSwR + ri;
-            const int qw = LB - kSwReach - Lfirst;                        // load index of the window's first block (may be < 0)
             const int ws = win_slot * kSwR;                               // its ring row
             const int wlo = (j - kSwReach) * kSwR;                        // first row of the window
             const int Grow0 = (LB - j) * kSwR;                            // linear row of this pair's row 0
@@ -336,17 +313,11 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
                         }
                 }
                 if (GRAD && RING && c0 == 0) {
-                    // REDs of the previous step are long performed by now: publish them to the retire warps (cheap
-                    // fence).  Then make sure the ring rows this step can hit are zero: the first kSwRingRows rows were
-                    // zeroed at the start, a later block re-uses the rows of block LB + kSwReach - kSwRingRows / kSwR,
-                    // which retire iteration t - kLag wrote back and zeroed (far behind: this wait never blocks)
+                    // the ring rows this step can hit must be zero: the first kSwRingRows rows were zeroed at the start, a
+                    // later block re-uses the rows of block LB + kSwReach - kSwRingRows / kSwR, which retire iteration
+                    // t - kLag wrote back and zeroed (far behind: this wait does not block)
                     constexpr int kLag = kSwRingRows / kSwR - 2 * kSwReach;
                     if (t == 0) mbar_wait(bar_zero, 0);
-                    else {
-                        fence_cta();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_reds + 8 * ((t - 1) & 3));
-                    }
                     if (t >= kLag) mbar_wait(bar_zero + 8 + 8 * ((t - kLag) & 3), (uint32_t)(((t - kLag) >> 2) & 1));
                 }
                 // ---- phase 4: blend (:226-227), residuals (:107-110), occlusion (:114), loss, gradients
@@ -420,18 +391,12 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
 #undef RGBD_BLEND
                 }
             }
-            // this step no longer needs the oldest block of the window
-            if (qw >= 0) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_empty + 8 * win_slot);
-            }
+            // step finished: the oldest block of the window is dead, the REDs of this step are issued (CTA-scope release)
+            if (GRAD && RING) fence_cta();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_done + 8 * (t & 3));
             own_slot = own_slot + 1 == kSwNB ? 0 : own_slot + 1;
             win_slot = win_slot + 1 == kSwNB ? 0 : win_slot + 1;
-        }
-        if (GRAD && RING && nsteps > 0) {
-            fence_cta();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_reds + 8 * ((nsteps - 1) & 3));
         }
         // ---- per-CTA partial sums (fixed order: warp shuffle tree, then rows 0..7 of each direction)
         s_rgb = warp_sum(s_rgb); s_d = warp_sum(s_d); s_h = warp_sum(s_h);
@@ -446,59 +411,73 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
             if (LOSS && a.hinge_partials) a.hinge_partials[(size_t)dir * ncta + cta] = h;
             if (GRAD && RING && dir == 0) a.ovf_count[cta] = *scount;
         }
-    } else if (GRAD && RING) {
-        // ------------------------------------------------------------------ retire: write back + zero behind the sweep
-        const int rw = warp - kSwComputeWarps - 1;
+    } else {
+        // ------------------------------------------------------------------ retire warps (warp 0, lane 0 also drives the TMA)
+        const int rw = warp - kSwComputeWarps;
+        const bool retire = GRAD && RING;
+        uint64_t policy = 0;
+        if (rw == 0 && lane == 0) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        // stream block L (kSwR rows of both images, 4 planes each) into its ring slot
+        auto load_block = [&](int L) {
+            constexpr uint32_t row_bytes = (uint32_t)(kSwR * W * sizeof(float));      // one plane of one block
+            const int slot = (L - Lfirst) % kSwNB;
+            const int p = L / a.bpp, j = L - p * a.bpp;
+            mbar_expect_tx(bar_full + 8 * slot, 8 * row_bytes);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const float *src = (s ? a.img_rot : a.img) + (size_t)p * 4 * HW + (size_t)j * kSwR * W;
+                const uint32_t dst = smem_u32(sring + (size_t)s * img_stride + (size_t)slot * kSwR * W);
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch)
+                    bulk_g2s(dst + ch * PSB, src + (size_t)ch * HW, row_bytes, bar_full + 8 * slot, policy);
+            }
+        };
+        if (rw == 0 && lane == 0) {                                       // fill the ring: every block no finished step frees
+            const int last0 = LBs + kSwNB - kSwReach - 1 < Llast ? LBs + kSwNB - kSwReach - 1 : Llast;
+            for (int L = Lfirst; L <= last0; ++L) load_block(L);
+        }
+        if (!retire && rw != 0) return;
         float scale = a.scale;
-        if (a.scale_dev) scale *= __ldg(a.scale_dev);
+        if (retire && a.scale_dev) scale *= __ldg(a.scale_dev);
         float4 *ring = a.ring + (size_t)cta * 2 * kSwRingRows * W;
-        constexpr int kAllItems = 2 * kSwR;                               // (image, row) items of a block
+        constexpr int kItems = 2 * kSwR / kSwRetireWarps;                 // (image, row) items of a block per warp
         auto zero_block = [&](int X) {
-            for (int item = rw; item < kAllItems; item += kSwRetireWarps) {
-                const int sel = item / kSwR, r = item % kSwR;
+#pragma unroll
+            for (int n = 0; n < kItems; ++n) {
+                const int item = rw * kItems + n, sel = item / kSwR, r = item % kSwR;
                 float4 *dst = ring + ((size_t)sel * kSwRingRows + ((X * kSwR + r) & (kSwRingRows - 1))) * W;
 #pragma unroll
                 for (int col = lane; col < W; col += 32) st_cg_zero_v4(dst + col);
             }
         };
-        // write back one finished block: all loads of two (image, row) items in flight, then zero the ring rows
-        // (same thread, same address: ordered) and store the four planes (coalesced 128-byte rows per warp)
+        // write back one finished block: ALL loads of the warp's (image, row) items in flight at once (one L2 round trip
+        // per block), then zero the ring rows (same thread, same address: ordered) and store the four planes
+        // (coalesced 128-byte rows per warp)
         auto retire_block = [&](int X) {
             const int p = X / a.bpp, j = X - p * a.bpp;
-            float *gp0 = a.g_img + (size_t)p * 4 * HW + (size_t)j * kSwR * W + lane;
-            float *gp1 = a.g_img_rot + (size_t)p * 4 * HW + (size_t)j * kSwR * W + lane;
-#pragma unroll 1
-            for (int it0 = rw; it0 < kAllItems; it0 += 2 * kSwRetireWarps) {
-                float4 v[2][W / 32];
+            float4 v[kItems][W / 32];
 #pragma unroll
-                for (int n = 0; n < 2; ++n) {
-                    const int item = it0 + n * kSwRetireWarps;
-                    if (item < kAllItems) {
-                        const int sel = item / kSwR, r = item % kSwR;
-                        const float4 *src = ring + ((size_t)sel * kSwRingRows + ((X * kSwR + r) & (kSwRingRows - 1))) * W + lane;
+            for (int n = 0; n < kItems; ++n) {
+                const int item = rw * kItems + n, sel = item / kSwR, r = item % kSwR;
+                const float4 *src = ring + ((size_t)sel * kSwRingRows + ((X * kSwR + r) & (kSwRingRows - 1))) * W + lane;
 #pragma unroll
-                        for (int k = 0; k < W / 32; ++k) v[n][k] = ld_cg_v4(src + 32 * k);
-                    }
-                }
+                for (int k = 0; k < W / 32; ++k) v[n][k] = ld_cg_v4(src + 32 * k);
+            }
 #pragma unroll
-                for (int n = 0; n < 2; ++n) {
-                    const int item = it0 + n * kSwRetireWarps;
-                    if (item < kAllItems) {
-                        const int sel = item / kSwR, r = item % kSwR;
-                        float4 *src = ring + ((size_t)sel * kSwRingRows + ((X * kSwR + r) & (kSwRingRows - 1))) * W + lane;
-                        float *dst = (sel ? gp1 : gp0) + r * W;
+            for (int n = 0; n < kItems; ++n) {
+                const int item = rw * kItems + n, sel = item / kSwR, r = item % kSwR;
+                float4 *src = ring + ((size_t)sel * kSwRingRows + ((X * kSwR + r) & (kSwRingRows - 1))) * W + lane;
+                float *dst = (sel ? a.g_img_rot : a.g_img) + (size_t)p * 4 * HW + (size_t)(j * kSwR + r) * W + lane;
 #pragma unroll
-                        for (int k = 0; k < W / 32; ++k) {
-                            st_cg_zero_v4(src + 32 * k);
-                            // written once, read by the caller's next kernels: streaming stores keep L2 for the ring
-                            __stcs(dst + 32 * k, v[n][k].x * scale); __stcs(dst + HW + 32 * k, v[n][k].y * scale);
-                            __stcs(dst + 2 * (size_t)HW + 32 * k, v[n][k].z * scale); __stcs(dst + 3 * (size_t)HW + 32 * k, v[n][k].w * scale);
-                        }
-                    }
+                for (int k = 0; k < W / 32; ++k) {
+                    st_cg_zero_v4(src + 32 * k);
+                    // written once, read by the caller's next kernels: streaming stores keep L2 for the ring
+                    __stcs(dst + 32 * k, v[n][k].x * scale); __stcs(dst + HW + 32 * k, v[n][k].y * scale);
+                    __stcs(dst + 2 * (size_t)HW + 32 * k, v[n][k].z * scale); __stcs(dst + 3 * (size_t)HW + 32 * k, v[n][k].w * scale);
                 }
             }
         };
-        {   // the ring rows of the first blocks (later blocks re-use rows that were zeroed behind the sweep)
+        if (retire) {   // the ring rows of the first blocks (later blocks re-use rows that were zeroed behind the sweep)
             const int nz = nsteps < kSwRingRows / kSwR ? nsteps : kSwRingRows / kSwR;
             for (int X = LBs; X < LBs + nz; ++X) zero_block(X);
             fence_cta();
@@ -507,14 +486,21 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
         }
 #pragma unroll 1
         for (int t = 0; t < nsteps; ++t) {
-            mbar_wait_relaxed(bar_reds + 8 * (t & 3), (uint32_t)((t >> 2) & 1));   // REDs of steps <= t are performed
-            const int Xr = LBs + t - kSwReach;                             // no later step can hit this block
-            if (Xr >= LBs) retire_block(Xr);
-            fence_cta();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_zero + 8 + 8 * (t & 3));
+            mbar_wait_relaxed(bar_done + 8 * (t & 3), (uint32_t)((t >> 2) & 1));   // every compute warp has finished step t
+            if (rw == 0 && lane == 0) {                                    // block LB - kSwReach is dead: its slot takes LB + 4
+                const int L = LBs + t + kSwNB - kSwReach;
+                if (L <= Llast) load_block(L);
+            }
+            if (retire) {
+                const int Xr = LBs + t - kSwReach;                         // no later step can hit this block's ring rows
+                if (Xr >= LBs) retire_block(Xr);
+                fence_cta();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_zero + 8 + 8 * (t & 3));
+            }
         }
-        for (int X = (LBe - kSwReach > LBs ? LBe - kSwReach : LBs); X < LBe; ++X) retire_block(X);
+        if (retire)
+            for (int X = (LBe - kSwReach > LBs ? LBe - kSwReach : LBs); X < LBe; ++X) retire_block(X);
     }
 }
 
