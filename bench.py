@@ -6,8 +6,10 @@
 
 One "step" = one pass of the hot path over one batch of B synthetic RGB-D pairs: the consistency
 loss (both warp directions, occlusion mask) AND the gradients w.r.t. both 4-channel images.
-Default workload = BASELINE.json configs[1] (ffhq_stylegan_occlusion.yml: batch 32 at 128x128,
-L1, occlusion on, lambda_geometric 3, poses from the yml's CameraParamPrior ranges).
+Default workload = BASELINE.json configs[4] at the metric's size: 256 pairs per GPU at 128x128 (L1,
+occlusion on, lambda_geometric 3, poses from ffhq_stylegan_occlusion.yml's CameraParamPrior ranges);
+configs[1] (32 pairs), configs[4] at 256x256 and configs[2] (car poses, 64 pairs in total) are
+timed the same way at every N and reported under "extra".
 
 Prints ONE JSON line (rank 0): metric/value (device-resident inputs, CUDA-event timed, max over
 ranks), e2e (public API, host buffers, H2D + D2H inside the timed region), roofline of the dominant
@@ -51,8 +53,8 @@ def _cpu_worker(args):
     """one fwd+bwd of the NumPy port (the Chainer CPU path's array work) on `pairs` pairs"""
     pairs, S, depth, seed, reps = args
     from oracle import numpy_port as npp
-    from rgbd_gan_b200 import poses
-    x, cam = poses.synthetic_batch(pairs, S, depth=depth, seed=seed)
+    from tools import synthetic
+    x, cam = synthetic.synthetic_batch(pairs, S, depth=depth, seed=seed)
     f = npp.LossFuncRotateNP(lambda_geometric=LAMBDA_GEO)
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -98,12 +100,6 @@ def run_reference(a):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
-
-
-def workload_config(a, pairs):
-    return {"workload": "configs[1] ffhq_stylegan_occlusion.yml consistency loss fwd+bwd, occlusion mask on, L1, "
-                        "lambda_geometric 3", "pairs_per_gpu": pairs, "size": a.size, "channels": 4,
-            "depth": a.depth, "pose_ranges": "x 0.3054 / y 1.0472 rad (yml)", "upstream_grad": LAMBDA_ROTATE}
 
 
 # ------------------------------------------------------------------------------------ clock sampler
@@ -154,215 +150,285 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------- GPU arm
-def run_ours(a):
-    import torch
-    import torch.distributed as dist
-    from rgbd_gan_b200 import _lib, poses
-    from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
+FFHQ, CAR = "ffhq", "car"
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-    B, S, C = a.pairs, a.size, 4
-    HW = S * S
-    hbm_peak, peak_src = peaks()
 
-    # ---- synthetic input pool, larger than L2, rotated between steps (no L2 reuse across steps)
-    bytes_per_set = 4 * B * C * HW * 4                       # 2 images in + 2 gradients out
-    pool_n = max(2, -(-3 * L2_BYTES // bytes_per_set))       # >= 3 x L2
-    pool_n = min(pool_n, 64)
-    sets = []
-    host_f = LossFuncRotate(None, lambda_geometric=LAMBDA_GEO)
-    host_f.init_params(None, size=S)
-    for s in range(min(pool_n, 8)):                          # 8 distinct contents are enough; more are copies
-        x, cam = poses.synthetic_batch(B, S, depth=a.depth, seed=1000 * rank + s)
-        M, c, Mi, ci = pose_algebra(host_f.K, host_f.inv_K, cam[:B], cam[B:])
-        sets.append((x, cam, np.concatenate([M.reshape(-1), c.reshape(-1), Mi.reshape(-1), ci.reshape(-1)])))
-    pool = []
-    for s in range(pool_n):
-        x, cam, pv = sets[s % len(sets)]
-        xt = torch.from_numpy(x).to(dev)
-        pool.append(dict(img=xt[:B].contiguous(), img_rot=xt[B:].contiguous(), poses=torch.from_numpy(pv).to(dev),
-                         g_img=torch.empty((B, C, S, S), device=dev), g_rot=torch.empty((B, C, S, S), device=dev),
-                         parts=torch.zeros(8, device=dev), red=torch.zeros(4, device=dev)))
-    ws = torch.empty(lib.rgbd_consistency_workspace_bytes(B, C, S, S), dtype=torch.uint8, device=dev)
-    peer = None
-    if world > 1 and a.collective == "peer":
-        from rgbd_gan_b200.distributed import PeerComm
-        peer = PeerComm()                 # fused 16-byte all-reduce inside the loss kernel (NVLink peer memory)
-    # N > 1: the loss exchange is deferred (joined once at the end of the timed region, inside it), so it
-    # overlaps the stage-out of its step and the stage-in of the next; gradients are never deferred
-    opts = _lib.LossOpts(_lib.NORM_L1, 1, float("nan"), float("nan"), LAMBDA_GEO, B * world,
-                         peer.handle if peer is not None else None, 1 if peer is not None else 0, 0)
-    stream = torch.cuda.Stream(device=dev)
-    sp = ctypes.c_void_p(stream.cuda_stream)
+class Harness:
+    """process-wide state of the GPU arm: device, stream, library, the loss collective (peer mailbox or NCCL)"""
 
-    def ptrs(e):
+    def __init__(self, a):
+        import torch
+        import torch.distributed as dist
+        from rgbd_gan_b200 import _lib
+        self.torch, self.dist, self._lib = torch, dist, _lib
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = _lib.load()
+        self.hbm_peak, self.peak_src = peaks()
+        self.peer = None
+        if self.world > 1 and a.collective == "peer":
+            from rgbd_gan_b200.distributed import PeerComm
+            self.peer = PeerComm()            # fused 20-byte all-reduce inside the finalize kernel (NVLink peer memory)
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.sp = ctypes.c_void_p(self.stream.cuda_stream)
+        self.comm = torch.cuda.Stream(device=self.dev) if (self.world > 1 and self.peer is None) else None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, v):
+        if self.world > 1:
+            t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            v = float(t.item())
+        return v
+
+
+class Workload:
+    """B pairs per GPU at SxS: a pool of input sets larger than L2 (rotated between steps), outputs, workspace, options"""
+
+    def __init__(self, h, B, S, depth="rough", ranges=FFHQ, lam=LAMBDA_GEO, n_global=None, hinge=None, K=None,
+                 max_depth=None, min_depth=None, label=""):
+        torch, _lib = h.torch, h._lib
+        from tools import synthetic as poses
+        from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
+        self.h, self.B, self.S, self.C, self.depth, self.lam, self.label = h, B, S, 4, depth, lam, label
+        C, HW = 4, S * S
+        self.bytes_per_set = 4 * B * C * HW * 4                  # 2 images in + 2 gradients out
+        self.pool_n = min(max(2, -(-3 * L2_BYTES // self.bytes_per_set)), 64)       # >= 3 x L2 in rotation
+        rg = poses.FFHQ_RANGES if ranges == FFHQ else poses.CAR_RANGES
+        hf = LossFuncRotate(None, K=K, lambda_geometric=lam)
+        hf.init_params(None, size=S)
+        self.host_sets, self.pool = [], []
+        for s in range(min(self.pool_n, 4)):                     # a few distinct contents; further sets are copies
+            x, cam = poses.synthetic_batch(B, S, depth=depth, ranges=rg, seed=1000 * h.rank + s)
+            M, c, Mi, ci = pose_algebra(hf.K, hf.inv_K, cam[:B], cam[B:])
+            self.host_sets.append((x, cam, np.concatenate([M.reshape(-1), c.reshape(-1), Mi.reshape(-1), ci.reshape(-1)])))
+        for s in range(self.pool_n):
+            x, cam, pv = self.host_sets[s % len(self.host_sets)]
+            xt = torch.from_numpy(x).to(h.dev)
+            self.pool.append(dict(img=xt[:B].contiguous(), img_rot=xt[B:].contiguous(), poses=torch.from_numpy(pv).to(h.dev),
+                                  g_img=torch.empty((B, C, S, S), device=h.dev), g_rot=torch.empty((B, C, S, S), device=h.dev),
+                                  parts=torch.zeros(8, device=h.dev), red=torch.zeros(4, device=h.dev)))
+            del xt
+        self.ws = torch.empty(h.lib.rgbd_consistency_workspace_bytes(B, C, S, S), dtype=torch.uint8, device=h.dev)
+        nan = float("nan")
+        ng = n_global if n_global is not None else B * h.world
+        # N > 1: the loss exchange is deferred (it overlaps the next call; joined at the end of the timed region,
+        # inside it); `joined` makes every call wait for its own exchange instead.  Gradients are never deferred
+        self.opts = _lib.LossOpts(_lib.NORM_L1, 1, nan if max_depth is None else max_depth,
+                                  nan if min_depth is None else min_depth, lam, ng,
+                                  h.peer.handle if h.peer is not None else None, 1 if h.peer is not None else 0, 0)
+        self.opts_local = _lib.LossOpts(_lib.NORM_L1, 1, nan if max_depth is None else max_depth,
+                                        nan if min_depth is None else min_depth, lam, ng, None, 0, 0)
+        if hinge is not None:
+            for o in (self.opts, self.opts_local):
+                o.hinge_depth_min, o.hinge_lambda = hinge
+        self.sweep_path = bool(h.lib.rgbd_consistency_uses_sweep(B, C, S, S))
+
+    def ptrs(self, e):
+        B = self.B
         base = e["poses"].data_ptr()
         return [ctypes.c_void_p(e["img"].data_ptr()), ctypes.c_void_p(e["img_rot"].data_ptr())] + \
                [ctypes.c_void_p(base + 4 * o) for o in (0, 9 * B, 12 * B, 21 * B)]
 
-    def step_fused(e):
-        _lib.call("rgbd_consistency_fwd_bwd", *ptrs(e), B, C, S, S, ctypes.byref(opts), ctypes.c_float(LAMBDA_ROTATE),
-                  ctypes.c_void_p(e["parts"].data_ptr()), None, ctypes.c_void_p(e["g_img"].data_ptr()),
-                  ctypes.c_void_p(e["g_rot"].data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp)
+    def step_fused(self, e, opts=None, parts=None):
+        h = self.h
+        h._lib.call("rgbd_consistency_fwd_bwd", *self.ptrs(e), self.B, self.C, self.S, self.S,
+                    ctypes.byref(opts or self.opts), ctypes.c_float(LAMBDA_ROTATE),
+                    ctypes.c_void_p((parts if parts is not None else e["parts"]).data_ptr()), None,
+                    ctypes.c_void_p(e["g_img"].data_ptr()), ctypes.c_void_p(e["g_rot"].data_ptr()),
+                    ctypes.c_void_p(self.ws.data_ptr()), self.ws.numel(), h.sp)
 
-    def step_two_pass(e):
-        _lib.call("rgbd_consistency_fwd", *ptrs(e), B, C, S, S, ctypes.byref(opts),
-                  ctypes.c_void_p(e["parts"].data_ptr()), None, None, ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp)
-        _lib.call("rgbd_consistency_bwd", *ptrs(e), B, C, S, S, ctypes.byref(opts), ctypes.c_float(LAMBDA_ROTATE), None,
-                  None, ctypes.c_void_p(e["g_img"].data_ptr()), ctypes.c_void_p(e["g_rot"].data_ptr()),
-                  ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp)
+    def step_two_pass(self, e):
+        h = self.h
+        h._lib.call("rgbd_consistency_fwd", *self.ptrs(e), self.B, self.C, self.S, self.S, ctypes.byref(self.opts),
+                    ctypes.c_void_p(e["parts"].data_ptr()), None, None, ctypes.c_void_p(self.ws.data_ptr()), self.ws.numel(), h.sp)
+        h._lib.call("rgbd_consistency_bwd", *self.ptrs(e), self.B, self.C, self.S, self.S, ctypes.byref(self.opts),
+                    ctypes.c_float(LAMBDA_ROTATE), None, None, ctypes.c_void_p(e["g_img"].data_ptr()),
+                    ctypes.c_void_p(e["g_rot"].data_ptr()), ctypes.c_void_p(self.ws.data_ptr()), self.ws.numel(), h.sp)
 
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    def free(self):
+        self.pool, self.ws = [], None
+        self.h.torch.cuda.empty_cache()
 
-    def allreduce(e):
-        """the only collective of the path: all-reduce(sum) of the 4 loss means.  The gradients do not
-        depend on it (denominators are global by construction), so it runs on a side stream and overlaps
-        the next step's kernels; the timed region ends with both streams drained."""
-        if world == 1 or peer is not None:
+    def join_exchange(self):
+        h = self.h
+        if h.peer is not None:
+            h._lib.check(h.lib.rgbd_peer_comm_wait(h.peer.handle, h.sp), "rgbd_peer_comm_wait")
+
+    def _nccl_allreduce(self, e):
+        """--collective nccl: the only collective of the path, all-reduce(sum) of the 4 loss means, on a side stream"""
+        h = self.h
+        if h.comm is None:
             return
+        torch = h.torch
         ev = torch.cuda.Event()
-        ev.record(stream)
-        comm.wait_event(ev)
-        with torch.cuda.stream(comm):
+        ev.record(h.stream)
+        h.comm.wait_event(ev)
+        with torch.cuda.stream(h.comm):
             e["red"].copy_(e["parts"][:4], non_blocking=True)
-            dist.all_reduce(e["red"])
+            h.dist.all_reduce(e["red"])
             e["comm_done"] = torch.cuda.Event()
-            e["comm_done"].record(comm)
+            e["comm_done"].record(h.comm)
 
-    def before_reuse(e):
-        if world > 1 and e.get("comm_done") is not None:
-            stream.wait_event(e["comm_done"])          # slot's previous all-reduce has consumed `parts`
+    def timed(self, steps, warmup, step=None, sampler=None):
+        """EXACTLY `steps` steps, CUDA events on the launch stream, max over ranks.  Sequence: `warmup` untimed steps,
+        barrier + device sync, ONE untimed step whose loss exchange is joined (at N > 1 every GPU leaves it within
+        microseconds of the others, so the ranks enter the timed region aligned and the NCCL barrier's exit skew stays
+        outside), e0, `steps` steps, join of the last exchange, e1, barrier + device sync."""
+        h, torch = self.h, self.h.torch
+        step = step or self.step_fused
+        pool, n = self.pool, self.pool_n
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(step, steps, warmup, graphs=None, sampler=None):
-        """EXACTLY `steps` steps between barrier+sync, CUDA events on the launch stream, max over ranks"""
-        with torch.cuda.stream(stream):
+        def one(k):
+            e = pool[k % n]
+            if h.comm is not None and e.get("comm_done") is not None:
+                h.stream.wait_event(e["comm_done"])              # slot's previous all-reduce has consumed `parts`
+            step(e)
+            self._nccl_allreduce(e)
+        with torch.cuda.stream(h.stream):
             for k in range(warmup):
-                before_reuse(pool[k % pool_n])
-                (graphs[k % pool_n].replay() if graphs else step(pool[k % pool_n]))
-                allreduce(pool[k % pool_n])
-            if comm is not None:
-                stream.wait_stream(comm)
-            barrier()
+                one(k)
+            if h.comm is not None:
+                h.stream.wait_stream(h.comm)
+            self.join_exchange()
+            h.barrier()
+            one(warmup)                                          # alignment step (untimed)
+            if h.comm is not None:
+                h.stream.wait_stream(h.comm)
+            self.join_exchange()
             if sampler:
                 sampler.start()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
+            e0.record(h.stream)
             for k in range(steps):
-                before_reuse(pool[k % pool_n])
-                (graphs[k % pool_n].replay() if graphs else step(pool[k % pool_n]))
-                allreduce(pool[k % pool_n])
-            if comm is not None:
-                stream.wait_stream(comm)               # the last all-reduces are inside the timed region
-            if peer is not None:
-                _lib.check(lib.rgbd_peer_comm_wait(peer.handle, sp), "rgbd_peer_comm_wait")   # join the last exchange
-            e1.record(stream)
-            barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+                one(warmup + 1 + k)
+            if h.comm is not None:
+                h.stream.wait_stream(h.comm)                     # the last all-reduces are inside the timed region
+            self.join_exchange()                                 # ... and so is the join of the last deferred exchange
+            e1.record(h.stream)
+            h.barrier()
+        return h.max_over_ranks(e0.elapsed_time(e1))
 
-    def capture(step):
-        gs = []
-        with torch.cuda.stream(stream):
-            for e in pool:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=stream):
-                    step(e)
-                gs.append(g)
-        return gs
+    def record(self, steps, warmup, step=None, sampler=None):
+        ms = self.timed(steps, warmup, step, sampler)
+        h = self.h
+        per_gpu = 24 * self.C * self.S * self.S * self.B * steps / (ms * 1e-3) / 1e9      # SURVEY 8(d): 24*C*H*W per pair
+        return {"pairs_per_gpu": self.B, "size": self.S, "depth": self.depth, "workload": self.label,
+                "value": h.world * self.B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+                "step_algorithmic_GBps_per_gpu": per_gpu, "frac_of_hbm_peak": per_gpu / h.hbm_peak,
+                "path": "row sweep (k_consistency_sweep + k_sweep_fixup)" if self.sweep_path
+                        else "three-kernel chain (stage-in, k_consistency_fast, stage-out)"}
 
-    # ---- launches per step (counted by the library) and clock pre-warm
-    with torch.cuda.stream(stream):
-        n0 = lib.rgbd_launch_count()
-        step_fused(pool[0])
-        launches_fused = lib.rgbd_launch_count() - n0
-        n0 = lib.rgbd_launch_count()
-        step_two_pass(pool[0])
-        launches_two = lib.rgbd_launch_count() - n0
-        torch.cuda.synchronize(dev)
-        for k in range(4000):                        # bring clocks up before anything is timed (fixed count:
-            step_fused(pool[k % pool_n])             # every rank must make the same sequence of loss calls)
-        torch.cuda.synchronize(dev)
+    def parity(self):
+        """N > 1: every rank also evaluates its shard WITHOUT the collective; rank 0 checks that the exchanged loss parts
+        are bit-for-bit the rank-ordered fp32 sum of the local parts (the exchange adds the mailbox slots in rank order)"""
+        h, torch = self.h, self.h.torch
+        if h.world == 1:
+            return None
+        e = self.pool[0]
+        loc = torch.zeros(8, device=h.dev)
+        with torch.cuda.stream(h.stream):
+            self.step_fused(e)
+            self.join_exchange()
+            if h.comm is not None:
+                self._nccl_allreduce(e)
+                h.stream.wait_stream(h.comm)
+            self.step_fused(e, opts=self.opts_local, parts=loc)
+        torch.cuda.synchronize(h.dev)
+        got = (e["red"] if h.comm is not None else e["parts"][:4]).clone()
+        allloc = [torch.zeros(8, device=h.dev) for _ in range(h.world)]
+        h.dist.all_gather(allloc, loc)
+        if h.rank != 0:
+            return None
+        locs = np.stack([t.cpu().numpy() for t in allloc]).astype(np.float32)
+        want = np.zeros(4, np.float32)
+        for r in range(h.world):
+            want = (want + locs[r, :4]).astype(np.float32)
+        gotn = got.cpu().numpy().astype(np.float32)
+        exact = bool(np.array_equal(gotn, want))
+        close = bool(np.allclose(gotn, want, rtol=1e-6, atol=0))
+        return {"ok": exact if h.peer is not None else close, "bit_exact": exact, "exchanged": [float(v) for v in gotn],
+                "sum_of_local_parts": [float(v) for v in want], "ranks": h.world,
+                "collective": "peer mailbox (rank-ordered fp32 sum)" if h.peer is not None else "NCCL all-reduce"}
 
-    # direct launches (PDL chain) are the default: measured 27.9 us/step vs 28.9 us/step for CUDA-graph replays
-    # of the same calls (profiles/r01_tuning.md); --graph switches to graph replays (not with a deferred exchange)
-    use_graph = a.graph and peer is None
-    graphs_fused = capture(step_fused) if use_graph else None
-    graphs_two = capture(step_two_pass) if use_graph else None
 
-    sampler = ClockSampler(local)
-    ms = timed(step_fused, a.steps, a.warmup, graphs_fused, sampler)
-    clocks = sampler.stop()
-    ms_two = timed(step_two_pass, a.steps, a.warmup, graphs_two)
-    value = world * B * a.steps / (ms * 1e-3)
-    value_two = world * B * a.steps / (ms_two * 1e-3)
-
-    # ---- roofline of the dominant kernel: k_consistency<4,LOSS,GRAD> timed live with CUDA events
-    # recorded by the library around that launch (rgbd_profile_hook), same steps, same pool rotation
-    kern_ms = []
-    with torch.cuda.stream(stream):
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+def kernel_roofline(wl, steps, step_ms_total):
+    """the dominant kernel timed live with CUDA events recorded by the library around that launch (rgbd_profile_hook)"""
+    h, torch = wl.h, wl.h.torch
+    B, C, HW = wl.B, wl.C, wl.S * wl.S
+    n = min(steps, 200)
+    with torch.cuda.stream(h.stream):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         for e0, e1 in evs:               # torch creates the cudaEvent lazily: record once to get a handle
-            e0.record(stream); e1.record(stream)
-        for k in range(a.steps):
-            lib.rgbd_profile_hook(ctypes.c_void_p(evs[k][0].cuda_event), ctypes.c_void_p(evs[k][1].cuda_event))
-            step_fused(pool[k % pool_n])
-        torch.cuda.synchronize(dev)
-        kern_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
-    kern_avg_ms = sum(kern_ms) / len(kern_ms)
-    with torch.cuda.stream(stream):      # same for the loss-only main kernel of the two-pass forward
-        for k in range(a.steps):
-            lib.rgbd_profile_hook(ctypes.c_void_p(evs[k][0].cuda_event), ctypes.c_void_p(evs[k][1].cuda_event))
-            e = pool[k % pool_n]
-            _lib.call("rgbd_consistency_fwd", *ptrs(e), B, C, S, S, ctypes.byref(opts),
-                      ctypes.c_void_p(e["parts"].data_ptr()), None, None, ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp)
-        torch.cuda.synchronize(dev)
-        kern_fwd_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs) / len(evs)
+            e0.record(h.stream); e1.record(h.stream)
+        for k in range(n):
+            h.lib.rgbd_profile_hook(ctypes.c_void_p(evs[k][0].cuda_event), ctypes.c_void_p(evs[k][1].cuda_event))
+            wl.step_fused(wl.pool[k % wl.pool_n])
+        wl.join_exchange()
+        torch.cuda.synchronize(h.dev)
+        kern_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs) / n
+        for k in range(n):               # same for the loss-only kernel of the two-pass forward
+            h.lib.rgbd_profile_hook(ctypes.c_void_p(evs[k][0].cuda_event), ctypes.c_void_p(evs[k][1].cuda_event))
+            e = wl.pool[k % wl.pool_n]
+            h._lib.call("rgbd_consistency_fwd", *wl.ptrs(e), B, C, wl.S, wl.S, ctypes.byref(wl.opts),
+                        ctypes.c_void_p(e["parts"].data_ptr()), None, None, ctypes.c_void_p(wl.ws.data_ptr()), wl.ws.numel(), h.sp)
+        wl.join_exchange()
+        torch.cuda.synchronize(h.dev)
+        kern_fwd_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs) / n
     alg_kernel = 16 * C * HW * B                     # reads both images once + writes both gradients once
     alg_step = 24 * C * HW * B                       # SURVEY 8(d): two-pass fwd+bwd definition, per pair 24*C*HW
-    achieved = alg_kernel / (kern_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_consistency<4,LOSS,GRAD> (project+gather+residual+scatter)",
-                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": kern_avg_ms, "kernel_ms_loss_only_variant": kern_fwd_ms,
-                "kernel_share_of_step": kern_avg_ms * a.steps / ms,
-                "algorithmic_bytes_per_launch": alg_kernel,
-                "step": {"algorithmic_bytes": alg_step, "achieved": world * alg_step * a.steps / (ms * 1e-3) / 1e9 / world,
-                         "frac": alg_step * a.steps / (ms * 1e-3) / 1e9 / hbm_peak,
-                         "note": "whole fwd+bwd step per GPU, 24*C*H*W bytes per pair (SURVEY 8d)"}}
+    achieved = alg_kernel / (kern_ms * 1e-3) / 1e9
+    name = ("k_consistency_sweep<128,L1,LOSS,GRAD,RING> (persistent TMA-fed row sweep: unproject+transform+reproject, "
+            "LDS gather, occlusion-masked residual, ring scatter + write-back)") if wl.sweep_path else \
+           "k_consistency_fast<LOSS,GRAD> (project+gather+residual+scatter on the staged NHWC copy)"
+    r = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": h.hbm_peak, "unit": "GB/s",
+         "frac": achieved / h.hbm_peak, "traffic": None, "peak_source": h.peak_src, "kernel_ms": kern_ms,
+         "kernel_ms_loss_only_variant": kern_fwd_ms, "kernel_share_of_step": kern_ms * steps / step_ms_total,
+         "algorithmic_bytes_per_launch": alg_kernel,
+         "step": {"algorithmic_bytes": alg_step, "achieved": alg_step * steps / (step_ms_total * 1e-3) / 1e9,
+                  "frac": alg_step * steps / (step_ms_total * 1e-3) / 1e9 / h.hbm_peak,
+                  "note": "whole fwd+bwd step per GPU, 24*C*H*W bytes per pair (SURVEY 8d)"}}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get("k_consistency_bytes_per_launch")
+            t = json.load(open(tr))
+            key = "sweep_256pairs_128" if wl.sweep_path else "k_consistency_bytes_per_launch"
+            ent = t.get(key)
+            if isinstance(ent, dict):
+                r["traffic"] = ent["dram_bytes_per_launch"] * B // ent["pairs"]
+                r["traffic_source"] = "%s (static: one ncu --set full capture, dram__bytes_read+write per launch, scaled " \
+                                      "from %d pairs; not measured live)" % (ent["source"], ent["pairs"])
+            elif ent is not None:
+                r["traffic"] = ent
+                r["traffic_source"] = "profiles/traffic.json (static, round-1 ncu capture of the chain's main kernel)"
         except Exception:            # noqa: BLE001
             pass
+    return r
 
-    # ---- e2e: public API (LossFuncRotate mirror + autograd), host buffers, H2D/D2H inside the timed region
-    f = LossFuncRotate(None, lambda_geometric=LAMBDA_GEO, grad_scale=LAMBDA_ROTATE, return_new_zp=False,
-                       process_group=dist.group.WORLD if (world > 1 and peer is None) else None, peer_comm=peer)
-    host_sets = []
-    for s in range(len(sets)):
-        x, cam, _ = sets[s]
-        host_sets.append((torch.from_numpy(x).pin_memory(), cam))
+
+def e2e_leg(h, wl, steps, warmup, with_grads):
+    """public API (LossFuncRotate mirror + autograd) with HOST buffers: every step copies its inputs pinned-host -> device
+    and reads the loss (and optionally both gradient tensors) back; wall clock, max over ranks"""
+    torch, dist = h.torch, h.dist
+    from rgbd_gan_b200.loss_functions import LossFuncRotate
+    B, C, S = wl.B, wl.C, wl.S
+    f = LossFuncRotate(None, lambda_geometric=wl.lam, grad_scale=LAMBDA_ROTATE, return_new_zp=False,
+                       process_group=dist.group.WORLD if (h.world > 1 and h.peer is None) else None, peer_comm=h.peer)
+    host_sets = [(torch.from_numpy(x).pin_memory(), cam) for x, cam, _ in wl.host_sets[:2]]
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
-
-    copy_stream = torch.cuda.Stream(device=dev)
-    dev_in = [torch.empty((2 * B, C, S, S), device=dev) for _ in range(2)]     # double-buffered device inputs
+    g_host = [torch.empty((B, C, S, S)).pin_memory() for _ in range(2)] if with_grads else None
+    copy_stream = torch.cuda.Stream(device=h.dev)
+    dev_in = [torch.empty((2 * B, C, S, S), device=h.dev) for _ in range(2)]     # double-buffered device inputs
     in_ready = [None, None]
 
     def h2d(k):
@@ -373,7 +439,7 @@ def run_ours(a):
             in_ready[k % 2] = torch.cuda.Event()
             in_ready[k % 2].record(copy_stream)
 
-    def e2e_step(k, last):
+    def step(k, last):
         _, cam = host_sets[k % len(host_sets)]
         torch.cuda.current_stream().wait_event(in_ready[k % 2])
         if not last:
@@ -383,106 +449,120 @@ def run_ours(a):
         img_rot = xd[B:].detach().requires_grad_(True)
         loss, _ = f(img, cam[:B], img_rot, cam[B:], occlusion_aware=True)
         (loss * LAMBDA_ROTATE).backward()
+        if with_grads:
+            g_host[0].copy_(img.grad, non_blocking=True)
+            g_host[1].copy_(img_rot.grad, non_blocking=True)
         loss_host.copy_(loss.detach(), non_blocking=False)               # D2H read of the step's result (blocks)
-        return img.grad
 
-    e2e_steps = min(a.steps, 100)
-    nw = max(3, min(a.warmup, 5))
+    nw = max(3, min(warmup, 5))
     h2d(0)
     for k in range(nw):
-        e2e_step(k, False)
-    torch.cuda.synchronize(dev)
-    barrier()
+        step(k, False)
+    torch.cuda.synchronize(h.dev)
+    h.barrier()
     t0 = time.perf_counter()
     h2d(nw)                      # (the copy issued by the last warm-up step is repeated inside the timed region)
-    for k in range(nw, nw + e2e_steps):
-        e2e_step(k, k == nw + e2e_steps - 1)
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e = {"value": world * B * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * B * C * HW * 4 + 24 * B * 4,
-           "d2h_bytes_per_step": 4, "steps": e2e_steps,
-           "pipeline": "step k+1's H2D (copy stream, double-buffered) overlaps step k's kernels; loss read back every step",
-           "api": "rgbd_gan_b200.loss_functions.LossFuncRotate(grad_scale=lambda_rotate, return_new_zp=False) + backward()"}
+    for k in range(nw, nw + steps):
+        step(k, k == nw + steps - 1)
+    torch.cuda.synchronize(h.dev)
+    dt = h.max_over_ranks(time.perf_counter() - t0)
+    d2h = 4 + (2 * B * C * S * S * 4 if with_grads else 0)
+    return {"value": h.world * B * steps / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * B * C * S * S * 4 + 24 * B * 4,
+            "d2h_bytes_per_step": d2h, "steps": steps,
+            "pipeline": "step k+1's H2D (copy stream, double-buffered) overlaps step k's kernels; loss%s read back every step"
+                        % (" and both gradient tensors" if with_grads else ""),
+            "api": "rgbd_gan_b200.loss_functions.LossFuncRotate(grad_scale=lambda_rotate, return_new_zp=False) + backward()"}
+
+
+def workload_config(a, pairs):
+    return {"workload": "configs[4] throughput sweep: %d RGB-D pairs per GPU at %dx%d, consistency loss fwd+bwd (both warp "
+                        "directions, occlusion mask on, L1, lambda_geometric 3, ffhq_stylegan_occlusion.yml pose ranges)"
+                        % (pairs, a.size, a.size), "pairs_per_gpu": pairs, "size": a.size, "channels": 4,
+            "depth": a.depth, "pose_ranges": "x 0.3054 / y 1.0472 rad (yml)", "upstream_grad": LAMBDA_ROTATE}
+
+
+PREWARM_STEPS = 1500            # fixed count (every rank makes the same sequence of loss calls): ~0.2 s at 256 pairs
+
+
+def run_ours(a):
+    h = Harness(a)
+    torch = h.torch
+    B, S = a.pairs, a.size
+    wl = Workload(h, B, S, depth=a.depth, label="headline")
+    with torch.cuda.stream(h.stream):
+        n0 = h.lib.rgbd_launch_count()
+        wl.step_fused(wl.pool[0])
+        launches_fused = h.lib.rgbd_launch_count() - n0
+        n0 = h.lib.rgbd_launch_count()
+        wl.step_two_pass(wl.pool[0])
+        launches_two = h.lib.rgbd_launch_count() - n0
+        wl.join_exchange()
+        torch.cuda.synchronize(h.dev)
+        for k in range(PREWARM_STEPS):               # bring clocks up before anything is timed
+            wl.step_fused(wl.pool[k % wl.pool_n])
+        wl.join_exchange()
+        torch.cuda.synchronize(h.dev)
+    sampler = ClockSampler(h.local)
+    ms = wl.timed(a.steps, a.warmup, sampler=sampler)
+    clocks = sampler.stop()
+    value = h.world * B * a.steps / (ms * 1e-3)
+    two_steps = max(3, min(a.steps, 200))
+    ms_two = wl.timed(two_steps, a.warmup, step=wl.step_two_pass)
+    roofline = kernel_roofline(wl, a.steps, ms)
+    parity = wl.parity()
+    e2e_steps = max(3, min(a.steps, 50))
+    e2e = e2e_leg(h, wl, e2e_steps, a.warmup, with_grads=False)
+    e2e["with_gradients_d2h"] = e2e_leg(h, wl, e2e_steps, a.warmup, with_grads=True)
+    wl.free()
+
+    # ---- the other BASELINE.json configurations, same timing method, every N
+    k_extra = max(3, min(a.steps, 200))
+    extra = {}
+    if not a.no_extra:
+        for name, kw in (("cfg1_32_pairs_per_gpu", dict(B=32, S=128, label="configs[1] ffhq_stylegan_occlusion.yml: 32 pairs per GPU")),
+                         ("cfg4_256_pairs_at_256", dict(B=256, S=256, label="configs[4]: 256 pairs per GPU at 256x256")),
+                         ("cfg2_car_64_pairs_total", dict(B=max(1, 64 // h.world), S=128, ranges=CAR, lam=1.0, n_global=max(1, 64 // h.world) * h.world,
+                                                          label="configs[2] dcgan_shapenet_car.yml: 64 pairs in total (strong scaling), car pose "
+                                                                "ranges (yaw +-pi), lambda_geometric 1"))):
+            w2 = Workload(h, kw.pop("B"), kw.pop("S"), depth=a.depth, **kw)
+            extra[name] = w2.record(k_extra, 3)
+            if name.startswith("cfg2"):
+                extra[name]["scaling"] = "strong"
+            w2.free()
 
     line = None
-    if rank == 0:
+    if h.rank == 0:
+        coll = "none" if h.world == 1 else (
+            "own finalize kernel exchanges them over NVLink peer memory on a side stream; deferred by one call, the last "
+            "one joined inside the timed region" if h.peer is not None else "NCCL on a side stream")
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": h.world, "steps": a.steps, "warmup": a.warmup,
+            "prewarm_steps": PREWARM_STEPS + 3, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(a, B), l2="input pool of %d sets x %.0f MB rotated between steps (> L2)"
-                           % (pool_n, bytes_per_set / 2 ** 20), cuda_graph=bool(use_graph),
-                           path="rgbd_consistency_fwd_bwd (one-pass fwd+bwd, upstream grad = lambda_rotate)",
-                           parallelism="dp%d (pairs sharded; 4-float loss all-reduce: %s)" % (
-                               world, "none" if world == 1 else ("own finalize kernel exchanges them over NVLink peer memory on a side stream, joined at the end of the timed region"
-                                                                 if peer is not None else "NCCL on a side stream"))),
-            "two_pass": {"value": value_two, "ms_per_step": ms_two / a.steps,
+                           % (wl.pool_n, wl.bytes_per_set / 2 ** 20), cuda_graph=False,
+                           path="rgbd_consistency_fwd_bwd (one-pass fwd+bwd, upstream grad = lambda_rotate): "
+                                + ("row sweep" if wl.sweep_path else "three-kernel chain"),
+                           parallelism="dp%d (pairs sharded; 4-float loss all-reduce: %s)" % (h.world, coll)),
+            "two_pass": {"value": h.world * B * two_steps / (ms_two * 1e-3), "ms_per_step": ms_two / two_steps,
                          "path": "rgbd_consistency_fwd + rgbd_consistency_bwd (recompute)"},
             "e2e": e2e, "gpu_launches": int(launches_fused * a.steps),
             "launches_per_step": {"fwd_bwd": int(launches_fused), "two_pass": int(launches_two)},
-            "roofline": roofline, "clocks": clocks,
+            "roofline": roofline, "clocks": clocks, "extra": extra,
         }
-    if peer is not None:
-        peer.close()
-    return line, dict(dev=dev, world=world, rank=rank, lib=lib, hbm_peak=hbm_peak)
+        if parity is not None:
+            line["parity"] = parity
+    return line, dict(dev=h.dev, world=h.world, rank=h.rank, lib=h.lib, hbm_peak=h.hbm_peak, harness=h)
 
 
-def sweep(a, ctx_, sizes=((128, 256), (256, 256)), graph_like=False, hinge=None):
-    """cfg4 of BASELINE.json: batch 256 at 128^2 and 256^2 (single GPU): pairs/s and step-level roofline.
-    Also used for the generator-like smooth-depth variant of the headline workload."""
-    import torch
-    from rgbd_gan_b200 import _lib, poses
-    from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
-    dev, lib = ctx_["dev"], ctx_["lib"]
+def sweep(a, ctx_, sizes, hinge=None, depth=None, **kw):
+    """single-GPU sub-records (smooth depth, depth hinge, the DeepVoxels updater's variant): same Workload / timing"""
+    h = ctx_["harness"]
     out = []
     for S, B in sizes:
-        C, HW = 4, S * S
-        x, cam = poses.synthetic_batch(B, S, depth=a.depth, seed=7)
-        hf = LossFuncRotate(None, lambda_geometric=LAMBDA_GEO)
-        hf.init_params(None, size=S)
-        M, c, Mi, ci = pose_algebra(hf.K, hf.inv_K, cam[:B], cam[B:])
-        pv = torch.from_numpy(np.concatenate([M.reshape(-1), c.reshape(-1), Mi.reshape(-1), ci.reshape(-1)])).to(dev)
-        xt = torch.from_numpy(x).to(dev)
-        n_sets = max(1, min(16, -(-3 * L2_BYTES // (4 * B * C * HW * 4))))      # rotate > 3 x L2 of in+out data
-        imgs = [(xt[:B].clone(), xt[B:].clone()) for _ in range(n_sets)]
-        g_img, g_rot = torch.empty((B, C, S, S), device=dev), torch.empty((B, C, S, S), device=dev)
-        parts = torch.zeros(8, device=dev)
-        ws = torch.empty(lib.rgbd_consistency_workspace_bytes(B, C, S, S), dtype=torch.uint8, device=dev)
-        opts = _lib.LossOpts(_lib.NORM_L1, 1, float("nan"), float("nan"), LAMBDA_GEO, B, None)
-        if hinge is not None:
-            opts.hinge_depth_min, opts.hinge_lambda = hinge
-        base = pv.data_ptr()
-        pp = [ctypes.c_void_p(base + 4 * o) for o in (0, 9 * B, 12 * B, 21 * B)]
-
-        def step(k):
-            im, ir = imgs[k % n_sets]
-            _lib.call("rgbd_consistency_fwd_bwd", ctypes.c_void_p(im.data_ptr()), ctypes.c_void_p(ir.data_ptr()), *pp,
-                      B, C, S, S, ctypes.byref(opts), ctypes.c_float(LAMBDA_ROTATE), ctypes.c_void_p(parts.data_ptr()),
-                      None, ctypes.c_void_p(g_img.data_ptr()), ctypes.c_void_p(g_rot.data_ptr()),
-                      ctypes.c_void_p(ws.data_ptr()), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
-        for k in range(3):
-            step(k)
-        torch.cuda.synchronize(dev)
-        n = 20 if B >= 128 else 200
-        for k in range(n_sets):
-            step(k)
-        torch.cuda.synchronize(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for k in range(n):
-            step(k)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1) / n
-        gbs = 24 * C * HW * B / (ms * 1e-3) / 1e9
-        out.append({"pairs": B, "size": S, "depth": a.depth, "pairs_per_s": B / (ms * 1e-3), "ms_per_step": ms,
-                    "step_algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / ctx_["hbm_peak"]})
-        del imgs, g_img, g_rot, ws, xt
-        torch.cuda.empty_cache()
+        w = Workload(h, B, S, depth=depth or a.depth, hinge=hinge, **kw)
+        out.append(w.record(20 if B >= 128 else 200, 3))
+        w.free()
     return out
 
 
@@ -491,7 +571,8 @@ def deepvoxels_bench(ctx_):
     Production geometry (deepvoxels_generator.py:229-253: G=32, F=32, 64x64x56, yml batch 10 -> run 16) and
     BASELINE's 64^3 volume.  Algorithmic bytes per sample fwd+bwd = 2*(F*G^3 + F*D*H*W)*4."""
     import torch
-    from rgbd_gan_b200 import _lib, poses
+    from rgbd_gan_b200 import _lib
+    from tools import synthetic as poses
     dev, lib = ctx_["dev"], ctx_["lib"]
     out = []
     for G, B in ((32, 16), (64, 16)):
@@ -500,8 +581,8 @@ def deepvoxels_bench(ctx_):
         vs = (1. / G) * 1.1 * 0.5
         P = _lib.DvParams(img, img, D, G, 128., 128., 32., 32., float(np.float32(vs)), float(np.float32(np.sqrt(3) / 4)))
         np.random.seed(3)
-        thetas = poses.CameraParamPrior.from_ranges(poses.CAR_RANGES, True).sample(2 * B)[:B]
-        cam = torch.from_numpy(poses.get_camera_matries(thetas).reshape(B, 16)).to(dev)
+        thetas = poses.sample_pose_pairs(B, poses.CAR_RANGES, True, np.random.default_rng(3))[:B]
+        cam = torch.from_numpy(poses.cam2world(thetas).reshape(B, 16)).to(dev)
         n = img * img * D
         n_sets = 3 if G == 32 else 2                     # rotate buffers: > L2 in total
         grids = [torch.randn((B, F, G, G, G), device=dev) for _ in range(n_sets)]
@@ -549,7 +630,8 @@ def render_bench(ctx_):
     replaces project + occlusion MLP + cumsum/clip/diff + collapse + depth map without materialising the (B,F,D,H,W)
     view volume.  Algorithmic bytes per sample fwd+bwd = 2*(F*G^3 + (F+2)*H*W)*4."""
     import torch
-    from rgbd_gan_b200 import _lib, poses
+    from rgbd_gan_b200 import _lib
+    from tools import synthetic as poses
     dev, lib = ctx_["dev"], ctx_["lib"]
     out = []
     for G, B in ((32, 16), (64, 16)):
@@ -560,8 +642,8 @@ def render_bench(ctx_):
         R = _lib.DvRenderParams(nf, D, 4.0, float(np.float32(np.sqrt(2) * np.sqrt(1.0 / (F + 1)))),
                                 float(np.float32(np.sqrt(2) * np.sqrt(1.0 / nf))))
         np.random.seed(3)
-        thetas = poses.CameraParamPrior.from_ranges(poses.CAR_RANGES, True).sample(2 * B)[:B]
-        cam = torch.from_numpy(poses.get_camera_matries(thetas).reshape(B, 16)).to(dev)
+        thetas = poses.sample_pose_pairs(B, poses.CAR_RANGES, True, np.random.default_rng(3))[:B]
+        cam = torch.from_numpy(poses.cam2world(thetas).reshape(B, 16)).to(dev)
         rng = np.random.default_rng(3)
         W1 = torch.from_numpy(rng.normal(size=(nf, F + 1)).astype(np.float32)).to(dev)
         b1 = torch.from_numpy(rng.normal(scale=0.3, size=(nf,)).astype(np.float32)).to(dev)
@@ -648,7 +730,8 @@ def feature_consistency_bench(a, ctx_):
     """the feature-space consistency loss of updater.py:345-354 (norm l2, C = 256 features +
     1 depth at 32x32, yml batch 32 -> 16 pairs); runs through the generic-C kernels (not tuned)."""
     import torch
-    from rgbd_gan_b200 import _lib, poses
+    from rgbd_gan_b200 import _lib
+    from tools import synthetic as poses
     from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
     dev, lib = ctx_["dev"], ctx_["lib"]
     B, C, S = 16, 257, 32
@@ -707,13 +790,14 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs", type=int, default=32)
+    ap.add_argument("--pairs", type=int, default=256)
     ap.add_argument("--size", type=int, default=128)
     ap.add_argument("--depth", default="rough", choices=["rough", "smooth"])
-    ap.add_argument("--graph", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="(ignored: direct PDL-chained launches are the measured default)")
     ap.add_argument("--no-graph", action="store_true", help="(default; kept for compatibility)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"])
-    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the single-GPU sub-records (DeepVoxels, hinge, ...)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configurations")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -737,17 +821,23 @@ def main():
         import torch.distributed as dist
         if line is not None:
             emit(line)
+        h = ctx_["harness"]
+        if h.peer is not None:
+            h.peer.close()
         dist.barrier()
         dist.destroy_process_group()
         return
     if not a.no_sweep:
-        line["sweep"] = sweep(a, ctx_)
         if a.depth == "rough":
-            a2 = argparse.Namespace(**vars(a))
-            a2.depth = "smooth"
-            line["smooth_depth"] = sweep(a2, ctx_, sizes=((a.size, a.pairs),), graph_like=False)[0]
+            line["smooth_depth"] = sweep(a, ctx_, sizes=((a.size, a.pairs),), depth="smooth", label="generator-like smooth depth")[0]
         # next row: the updaters' depth hinge (yml: depth_min 1.0, lambda_depth 10) fused in
-        line["with_depth_hinge"] = sweep(a, ctx_, sizes=((a.size, a.pairs),), hinge=(1.0, 10.0))[0]
+        line["with_depth_hinge"] = sweep(a, ctx_, sizes=((a.size, a.pairs),), hinge=(1.0, 10.0), label="depth hinge fused")[0]
+        # the DeepVoxels updater's call (updater_deepvoxels.py:176-190): 64x64, K = projection intrinsic, depth-range masks
+        Kdv = np.array([[128., 0, 32., 0], [0, 128., 32., 0], [0, 0, 1, 0], [0, 0, 0, 1]], np.float32)
+        line["dv_updater_64_depth_masks"] = sweep(a, ctx_, sizes=((64, 1024),), K=Kdv, max_depth=3.0, min_depth=0.2, ranges=CAR,
+                                                  label="updater_deepvoxels.py:176-190: 64x64, K given, max/min depth masks")[0]
+        line["dv_updater_64_no_masks"] = sweep(a, ctx_, sizes=((64, 1024),), K=Kdv, ranges=CAR,
+                                               label="same without the depth-range masks")[0]
         line["deepvoxels"] = deepvoxels_bench(ctx_)
         line["deepvoxels_render_fused"] = render_bench(ctx_)
         line["feature_consistency_c257"] = feature_consistency_bench(a, ctx_)

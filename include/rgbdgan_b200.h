@@ -96,6 +96,11 @@ typedef struct {
  */
 
 RGBD_API size_t rgbd_consistency_workspace_bytes(int B, int C, int H, int W);
+/* 1 if the plain entry points (no new_zp / masks output, no upstream new_zp gradient) run the persistent row-sweep
+ * kernel for this shape on the current device (C == 4, W in {64, 128}, H % 8 == 0 and enough rows per SM; env
+ * RGBD_B200_SWEEP = 0 | 1 | 2 overrides the automatic choice), 0 if they run the three-kernel chain.  Both paths
+ * implement the same reference lines (common/loss_functions.py:63-146,171-228); this is reporting only. */
+RGBD_API int rgbd_consistency_uses_sweep(int B, int C, int H, int W);
 
 /* Health check of the single-launch pipeline kernel (C == 4 path): the first bytes of the workspace
  * are its control block (ticket and per-pair dependency counters; all-zero between calls, initialised by the

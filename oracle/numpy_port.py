@@ -63,6 +63,28 @@ def sample_camera_prior(batch_size, ranges, uniform=False):
     return thetas.astype("float32")
 
 
+FFHQ_RANGES = (0.3054, 1.0472, 0, 0, 0, 0)          # configs/ffhq_stylegan_occlusion.yml:37-43
+CAR_RANGES = (0.3054, 3.1415, 0, 0, 0, 0)           # configs/dcgan_shapenet_car.yml:38-44
+
+
+def synthetic_batch(B, S, C=4, depth="rough", ranges=FFHQ_RANGES, uniform=None, seed=0):
+    """The synthetic workload of SURVEY.md 8(d) for the parity tests: 2B images (B pairs) + their cam2world matrices,
+    poses replayed through the reference's own generators above.  RGB ~ U(-1,1); depth "rough" ~ U(0.7,1.5) or
+    "smooth" = 1 + 0.1 sin(col/20).  Returns x (2B,C,S,S) fp32 and cam (2B,4,4) fp32; img = x[:B], img_rot = x[B:]."""
+    np.random.seed(seed)
+    cam = get_camera_matries(sample_camera_prior(2 * B, ranges, bool(uniform)))
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-1, 1, size=(2 * B, C, S, S)).astype("float32")
+    if depth == "rough":
+        x[:, -1] = rng.uniform(0.7, 1.5, size=(2 * B, S, S))
+    elif depth == "smooth":
+        col = np.arange(S, dtype="float32")[None, None, :]
+        x[:, -1] = 1 + 0.1 * np.sin(col / 20 * (128.0 / S))
+    else:
+        raise ValueError(depth)
+    return x, cam
+
+
 # ------------------------------------------------------------------------ consistency loss
 class LossFuncRotateNP:
     """common/loss_functions.py:31-146 with a hand-written reverse pass."""

@@ -3,7 +3,6 @@
 Public surface mirrors the reference modules it replaces:
   rgbd_gan_b200.loss_functions  <- common/loss_functions.py  (LossFuncRotate, warp, inv_warp, bilinear)
   rgbd_gan_b200.projection      <- deepvoxel/projection.py + deepvoxel/deepvoxel.py:388-433
-  rgbd_gan_b200.poses           <- updater.py:26-60, train_rgbd.py:192-217 (host-side pose inputs)
 All compute goes through include/rgbdgan_b200.h (librgbdgan_b200.so); there is no CPU fallback.
 """
 __version__ = "0.1.0"

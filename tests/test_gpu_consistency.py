@@ -228,7 +228,7 @@ def test_full_size_against_oracle_and_properties(S, B, depth, oracle_mod):
     oracle plus size-independent properties: linearity in gy, batch-permutation equivariance,
     fused == two-pass, run-to-run reproducibility bound of the atomics."""
     from gpu_util import Consistency
-    from rgbd_gan_b200 import poses
+    from oracle import numpy_port as poses
     from oracle import numpy_port as npp
     x, cam = poses.synthetic_batch(B, S, depth=depth, seed=11)
     port = npp.LossFuncRotateNP(lambda_geometric=3)
@@ -274,7 +274,7 @@ def test_identity_pose_closed_form():
     and the in-bounds mask is exactly the interior (strict `< H-1`).  The loss then has a closed
     form that torch evaluates at full 128^2 size."""
     from gpu_util import Consistency, DEV
-    from rgbd_gan_b200 import poses
+    from oracle import numpy_port as poses
     from oracle import numpy_port as npp
     B, S = 16, 128
     x, _ = poses.synthetic_batch(B, S, depth="rough", seed=5)

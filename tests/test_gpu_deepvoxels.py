@@ -81,14 +81,15 @@ def test_projection_against_reference_golden(name, monkeypatch):
 def test_full_size_against_oracle(G, F, B, exact, oracle_mod, monkeypatch):
     """production geometry (deepvoxels_generator.py:229-253: G=32, F=32, 64x64x56) and BASELINE's 64^3"""
     from gpu_util import DEV, dev, p, stream
-    from rgbd_gan_b200 import _lib, poses
+    from rgbd_gan_b200 import _lib
+    from oracle import numpy_port as poses
     monkeypatch.setenv("RGBD_B200_DV_EXACT", exact)
     img = 64
     D = int(np.ceil(np.sqrt(3) * G))
     vs = (1. / G) * 1.1 * 0.5
     K = np.array([[128., 0, 32., 0], [0, 128., 32., 0], [0, 0, 1, 0], [0, 0, 0, 1]])
     np.random.seed(3)
-    thetas = poses.CameraParamPrior.from_ranges(poses.CAR_RANGES, True).sample(2 * B)[:B]
+    thetas = poses.sample_camera_prior(2 * B, poses.CAR_RANGES, True)[:B]
     cam = poses.get_camera_matries(thetas)
     rng = np.random.default_rng(3)
     grid = rng.normal(size=(B, F, G, G, G)).astype(np.float32)

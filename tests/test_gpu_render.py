@@ -100,13 +100,13 @@ def test_render_mirror_like_the_generator(name):
 @pytest.mark.parametrize("G,B", [(32, 2)])
 def test_render_full_size_against_oracle_and_properties(G, B, oracle_mod):
     """production geometry (deepvoxels_generator.py:229-253: G=32, F=32, 64x64x56, nf 4, threshold 4)"""
-    from rgbd_gan_b200 import poses
+    from oracle import numpy_port as poses
     img, F, nf, thr = 64, 32, 4, 4.0
     D = int(np.ceil(np.sqrt(3) * G))
     vs, near = (1. / G) * 1.1 * 0.5, np.sqrt(3) / 4
     K = np.array([[128., 0, 32., 0], [0, 128., 32., 0], [0, 0, 1, 0], [0, 0, 0, 1]])
     np.random.seed(5)
-    thetas = poses.CameraParamPrior.from_ranges(poses.CAR_RANGES, True).sample(2 * B)[:B]
+    thetas = poses.sample_camera_prior(2 * B, poses.CAR_RANGES, True)[:B]
     cam = poses.get_camera_matries(thetas)
     rng = np.random.default_rng(5)
     grid = rng.normal(size=(B, F, G, G, G)).astype(np.float32)

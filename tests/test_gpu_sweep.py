@@ -16,7 +16,7 @@ torch = pytest.importorskip("torch")
 
 
 def _problem(B, S, depth, seed, ranges=None, wild=False):
-    from rgbd_gan_b200 import poses
+    from oracle import numpy_port as poses
     from oracle import numpy_port as npp
     kw = {} if ranges is None else dict(ranges=ranges)
     x, cam = poses.synthetic_batch(B, S, depth=depth, seed=seed, **kw)

@@ -2,7 +2,7 @@
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from rgbd_gan_b200 import poses
+from tools import synthetic as poses
 from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
 B, S = 32, 128
 x, cam = poses.synthetic_batch(B, S, seed=0)

@@ -2,7 +2,8 @@
 import ctypes, sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from rgbd_gan_b200 import _lib, poses
+from rgbd_gan_b200 import _lib
+from tools import synthetic as poses
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 planar = len(sys.argv) > 3
@@ -10,8 +11,8 @@ F, img = 32, 64
 D = int(np.ceil(np.sqrt(3) * G)); vs = (1. / G) * 1.1 * 0.5
 P = _lib.DvParams(img, img, D, G, 128., 128., 32., 32., float(np.float32(vs)), float(np.float32(np.sqrt(3) / 4)))
 np.random.seed(3)
-th = poses.CameraParamPrior.from_ranges(poses.CAR_RANGES, True).sample(2 * B)[:B]
-cam = torch.from_numpy(poses.get_camera_matries(th).reshape(B, 16)).cuda()
+th = poses.sample_pose_pairs(B, poses.CAR_RANGES, True)[:B]
+cam = torch.from_numpy(poses.cam2world(th).reshape(B, 16)).cuda()
 n = img * img * D
 lib = _lib.load()
 grid = torch.randn((B, F, G, G, G), device="cuda"); fr = torch.empty((B, F, n), device="cuda"); gg = torch.empty((B, F, G ** 3), device="cuda")

@@ -12,7 +12,8 @@ import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from rgbd_gan_b200 import _lib, poses
+from rgbd_gan_b200 import _lib
+from tools import synthetic as poses
 from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
 
 dev = torch.device("cuda", 0)

@@ -7,7 +7,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
-from rgbd_gan_b200 import _lib, poses
+from rgbd_gan_b200 import _lib
+from tools import synthetic as poses
 from rgbd_gan_b200.loss_functions import LossFuncRotate, pose_algebra
 
 B = int(os.environ.get("PAIRS", "32")); S = int(os.environ.get("SIZE", "128")); C = 4
