@@ -172,6 +172,14 @@ RGBD_API int rgbd_peer_comm_connect(void *comm, const unsigned char *all_handles
 RGBD_API int rgbd_peer_comm_destroy(void *comm);
 /* make `stream` wait for the most recent (deferred) loss exchange of this comm */
 RGBD_API int rgbd_peer_comm_wait(void *comm, void *stream);
+/* Health of the exchange: every wait for a peer's flag inside the finalize kernel is bounded (2 s, env
+ * RGBD_B200_PEER_TIMEOUT_MS); a wait that expires -- a rank died, or made a different sequence of loss calls --
+ * raises a sticky flag instead of hanging every GPU of the box, and the loss parts of that call are undefined.
+ * Synchronises the comm's side stream and `stream`; *status_host = 0 ok, 1 a wait timed out. */
+RGBD_API int rgbd_peer_comm_status(void *comm, void *stream, int *status_host);
+/* Test aid: instead of rgbd_peer_comm_connect, point every OTHER rank's mailbox at a local buffer nobody writes
+ * (single process, single GPU): the next sharded loss call then exercises the bounded wait. */
+RGBD_API int rgbd_debug_peer_comm_loopback(void *comm);
 
 /* ---- free functions of common/loss_functions.py ------------------------------------------ */
 

@@ -55,6 +55,8 @@ SIGNATURES = {
     "rgbd_peer_comm_connect": (c_int, [c_void, ctypes.c_char_p]),
     "rgbd_peer_comm_destroy": (c_int, [c_void]),
     "rgbd_peer_comm_wait": (c_int, [c_void, c_void]),
+    "rgbd_peer_comm_status": (c_int, [c_void, c_void, ctypes.POINTER(c_int)]),
+    "rgbd_debug_peer_comm_loopback": (c_int, [c_void]),
     "rgbd_consistency_workspace_bytes": (c_size, [c_int, c_int, c_int, c_int]),
     "rgbd_consistency_uses_sweep": (c_int, [c_int, c_int, c_int, c_int]),
     "rgbd_consistency_status": (c_int, [c_void, c_void, ctypes.POINTER(c_int)]),

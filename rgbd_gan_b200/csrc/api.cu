@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -65,6 +66,11 @@ RGBD_API int rgbd_peer_comm_create(int rank, int world, void **comm_out, unsigne
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     memcpy(ipc_handle_out, &h, 64);
     pc->args.rank = rank; pc->args.world = world; pc->args.box[rank] = pc->mine;
+    {   // RGBD_B200_PEER_TIMEOUT_MS (default 2000): bound of every wait for a peer's flag inside the finalize kernel
+        const char *e = getenv("RGBD_B200_PEER_TIMEOUT_MS");
+        const long ms = e && *e ? atol(e) : 2000;
+        pc->args.timeout_ns = (unsigned long long)(ms > 0 ? ms : 2000) * 1000000ull;
+    }
     e = cudaStreamCreateWithFlags(&pc->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pc->ev_main_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pc->ev_fin_done, cudaEventDisableTiming);
@@ -99,8 +105,10 @@ RGBD_API int rgbd_peer_comm_destroy(void *comm)
     using namespace rgbd;
     rgbd_peer_comm *pc = (rgbd_peer_comm *)comm;
     if (!pc) return 0;
-    for (int r = 0; r < pc->args.world; ++r)
-        if (r != pc->args.rank && pc->args.box[r]) cudaIpcCloseMemHandle(pc->args.box[r]);
+    for (int r = 0; r < pc->args.world; ++r) {
+        if (pc->loopback[r]) cudaFree(pc->loopback[r]);
+        else if (r != pc->args.rank && pc->args.box[r]) cudaIpcCloseMemHandle(pc->args.box[r]);
+    }
     if (pc->side) { cudaStreamSynchronize(pc->side); cudaStreamDestroy(pc->side); }
     if (pc->ev_main_done) cudaEventDestroy(pc->ev_main_done);
     if (pc->ev_fin_done) cudaEventDestroy(pc->ev_fin_done);
@@ -117,6 +125,36 @@ RGBD_API int rgbd_peer_comm_wait(void *comm, void *stream)
     if (!pc->fin_pending) return 0;
     const cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, pc->ev_fin_done, 0);
     if (e != cudaSuccess) { set_error("rgbd_peer_comm_wait: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
+RGBD_API int rgbd_peer_comm_status(void *comm, void *stream, int *status_host)
+{
+    using namespace rgbd;
+    rgbd_peer_comm *pc = (rgbd_peer_comm *)comm;
+    if (!pc || !status_host) { set_error("rgbd_peer_comm_status: null argument"); return RGBD_E_ARG; }
+    if (pc->side) cudaStreamSynchronize(pc->side);
+    unsigned err = 0;
+    cudaError_t e = cudaMemcpyAsync(&err, &pc->mine->error, sizeof(err), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) { set_error("rgbd_peer_comm_status: %s", cudaGetErrorString(e)); return (int)e; }
+    *status_host = err ? 1 : 0;
+    return 0;
+}
+
+RGBD_API int rgbd_debug_peer_comm_loopback(void *comm)
+{
+    using namespace rgbd;
+    rgbd_peer_comm *pc = (rgbd_peer_comm *)comm;
+    if (!pc || pc->connected) { set_error("rgbd_debug_peer_comm_loopback: null or already connected comm"); return RGBD_E_ARG; }
+    for (int r = 0; r < pc->args.world; ++r) {
+        if (r == pc->args.rank) continue;
+        cudaError_t e = cudaMalloc((void **)&pc->loopback[r], sizeof(rgbd_mailbox));
+        if (e == cudaSuccess) e = cudaMemset(pc->loopback[r], 0, sizeof(rgbd_mailbox));
+        if (e != cudaSuccess) { set_error("rgbd_debug_peer_comm_loopback: %s", cudaGetErrorString(e)); return (int)e; }
+        pc->args.box[r] = pc->loopback[r];
+    }
+    pc->connected = true;
     return 0;
 }
 

@@ -27,11 +27,13 @@ struct rgbd_mailbox {
     float slot[2][kMaxPeers][8];      // [epoch parity][writer rank][4 loss means, depth hinge, 3 spare]
     unsigned flag[2][kMaxPeers];      // epoch published by each writer
     unsigned epoch;                   // local: last completed epoch
-    unsigned pad[31];
+    unsigned error;                   // local, sticky: a wait for a peer's flag ran into the time limit
+    unsigned pad[30];
 };
 struct PeerArgs {
     rgbd_mailbox *box[kMaxPeers];     // box[r] = rank r's mailbox, mapped into this process
     int rank, world;
+    unsigned long long timeout_ns;    // bound of every wait for a peer (a dead / desynchronised rank must not hang the GPU)
 };
 struct rgbd_peer_comm {               // host object behind the opaque handle of the C-ABI
     PeerArgs args;
@@ -42,6 +44,7 @@ struct rgbd_peer_comm {               // host object behind the opaque handle of
     cudaEvent_t ev_main_done, ev_fin_done;
     bool fin_pending;                 // ev_fin_done has been recorded and not yet waited on by the main stream
     unsigned long long calls;         // parity selects one of two partial-sum buffers
+    rgbd_mailbox *loopback[kMaxPeers]; // test aid (rgbd_debug_peer_comm_loopback): local stand-ins for absent peers
 };
 
 struct Pose {          // one warp direction of one pair

@@ -48,6 +48,15 @@ class PeerComm:
         st = torch.cuda.current_stream() if stream is None else stream
         _lib.check(_lib.load().rgbd_peer_comm_wait(self._h, ctypes.c_void_p(st.cuda_stream)), "rgbd_peer_comm_wait")
 
+    def status(self, stream=None):
+        """0 = every exchange so far completed; 1 = a wait for a peer ran into the time limit (a rank died or made a
+        different sequence of loss calls): the loss parts of that call are undefined.  Synchronises."""
+        st = torch.cuda.current_stream() if stream is None else stream
+        out = ctypes.c_int(-1)
+        _lib.check(_lib.load().rgbd_peer_comm_status(self._h, ctypes.c_void_p(st.cuda_stream), ctypes.byref(out)),
+                   "rgbd_peer_comm_status")
+        return out.value
+
     def close(self):
         if self._h:
             torch.cuda.synchronize()

@@ -15,15 +15,8 @@ import torch
 
 from . import _lib
 from ._lib import DvParams, LossOpts  # noqa: F401
-
-
-def _as_numpy(a):
-    """theta / K style inputs: ndarray, torch tensor (any device), or an object with `.array`."""
-    if hasattr(a, "array") and not isinstance(a, np.ndarray):
-        a = a.array
-    if isinstance(a, torch.Tensor):
-        a = a.detach().cpu().numpy()
-    return np.asarray(a)
+from .host_math import as_numpy as _as_numpy
+from .host_math import combine_loss_parts, grid_dims as _grid_dims, intrinsics_for_size, pixel_grid, pose_algebra, warp_constants
 
 
 def _ptr(t):
@@ -40,25 +33,6 @@ def _dev_f32(t, what):
     if t.dtype != torch.float32:
         raise TypeError("%s must be float32, got %s" % (what, t.dtype))
     return t if t.is_contiguous() else t.contiguous()
-
-
-def pose_algebra(K, inv_K, theta, theta_rot):
-    """common/loss_functions.py:85-91 and the constant factors of warp (:174) / inv_warp (:181),
-    evaluated with the same NumPy matmul sequence on the host.
-    Returns float32 arrays M (B,3,3), c (B,3,1), Mi (B,3,3), ci (B,3,1) with the convention of
-    include/rgbdgan_b200.h: new_zp = M (z p) - c ; new_zp_rot = Mi (z_rot p) - ci  (ci = -(K t))."""
-    theta, theta_rot = _as_numpy(theta), _as_numpy(theta_rot)
-    R1, R2 = theta[:, :3, :3], theta_rot[:, :3, :3]
-    t1, t2 = theta[:, :3, -1:], theta_rot[:, :3, -1:]
-    R = np.matmul(R2.transpose(0, 2, 1), R1).astype("float32")
-    inv_R = R.transpose(0, 2, 1)
-    t = np.matmul(R1.transpose(0, 2, 1), t2 - t1).astype("float32")
-    M = np.matmul(np.matmul(K, R), inv_K)
-    c = np.matmul(np.matmul(K, R), t)
-    Mi = np.matmul(np.matmul(K, inv_R), inv_K)
-    ci = -np.matmul(K, t)
-    return (np.ascontiguousarray(M, dtype=np.float32), np.ascontiguousarray(c, dtype=np.float32),
-            np.ascontiguousarray(Mi, dtype=np.float32), np.ascontiguousarray(ci, dtype=np.float32))
 
 
 class _PoseUploader:
@@ -209,22 +183,9 @@ class LossFuncRotate:
 
     # -- :39-61
     def init_params(self, xp=None, size=4):
-        if self.size is None:
-            if self.K is not None:
-                self.K = np.array(_as_numpy(self.K)[:3, :3], "float32")
-                self.K[:2] *= size / self.K[0, 2] / 2
-                self.size = size
-            else:
-                self.size = size
-                self.K = np.array([[size * 2, 0, size / 2],
-                                   [0, size * 2, size / 2],
-                                   [0, 0, 1]], dtype="float32")
-        else:
-            self.size = size
-            self.K[:2] *= size / self.K[0, 2] / 2          # in place: state carries across stages (quirk Q9)
-        self.inv_K = np.linalg.inv(self.K).astype("float32")
-        self.p = np.asarray(list(np.meshgrid(np.arange(size), np.arange(size))) + [np.ones((size, size))],
-                            dtype="float32").reshape(3, -1)
+        self.K, self.inv_K = intrinsics_for_size(self.K, size, first=self.size is None)   # in place after the first call (Q9)
+        self.size = size
+        self.p = pixel_grid(size)
 
     def _workspace(self, B, C, H, W, device):
         key = (B, C, H, W, str(device))
@@ -323,13 +284,6 @@ class LossFuncRotate:
         return torch.nn.functional.binary_cross_entropy_with_logits(occupancy_field, label)
 
 
-def combine_loss_parts(parts, lambda_geometric):
-    """loss = (rgb + rgb_rot) + (depth*lambda + depth_rot*lambda), fp32 (:141-144).
-    `parts`: tensor/array of the four means (summed over shards)."""
-    lam = float(lambda_geometric)
-    return (parts[0] + parts[1]) + (parts[2] * lam + parts[3] * lam)
-
-
 # ------------------------------------------------------------------------------ free functions
 class _WarpFn(torch.autograd.Function):
     @staticmethod
@@ -352,31 +306,17 @@ class _WarpFn(torch.autograd.Function):
         return gz.reshape(ctx.zshape), None, None, None, None
 
 
-def _grid_dims(p, hw):
-    p = _as_numpy(p)
-    if p.shape != (3, hw):
-        raise ValueError("p must be (3, H*W)")
-    W, H = int(p[0].max()) + 1, int(p[1].max()) + 1
-    if W * H != hw:
-        raise ValueError("p is not a full pixel grid")
-    return H, W
-
-
 def warp(K, inv_K, R, t, z, p):
     """common/loss_functions.py:171-175: (K R K^-1)(z p) - (K R) t, returned as (B,HW,3). Differentiable in z."""
-    K, inv_K, R, t = (_as_numpy(a).astype("float32") for a in (K, inv_K, R, t))
     H, W = _grid_dims(p, z.shape[-1])
-    M = np.ascontiguousarray(np.matmul(np.matmul(K, R), inv_K), dtype=np.float32)
-    cv = np.ascontiguousarray(np.matmul(np.matmul(K, R), t), dtype=np.float32)
+    M, cv = warp_constants(K, inv_K, R, t, inverse=False)
     return _WarpFn.apply(z, torch.from_numpy(M).to(z.device), torch.from_numpy(cv).to(z.device), H, W)
 
 
 def inv_warp(K, inv_K, inv_R, t, z, p):
     """common/loss_functions.py:178-182: (K R^T K^-1)(z p) + K t, returned as (B,HW,3). Differentiable in z."""
-    K, inv_K, inv_R, t = (_as_numpy(a).astype("float32") for a in (K, inv_K, inv_R, t))
     H, W = _grid_dims(p, z.shape[-1])
-    M = np.ascontiguousarray(np.matmul(np.matmul(K, inv_R), inv_K), dtype=np.float32)
-    cv = np.ascontiguousarray(-np.matmul(K, t), dtype=np.float32)
+    M, cv = warp_constants(K, inv_K, inv_R, t, inverse=True)
     return _WarpFn.apply(z, torch.from_numpy(M).to(z.device), torch.from_numpy(cv).to(z.device), H, W)
 
 

@@ -80,7 +80,13 @@ class OracleBackedLib:
 
     def load(self):
         return types.SimpleNamespace(rgbd_consistency_workspace_bytes=lambda B, C, H, W: 1024,
-                                     rgbd_dv_render_workspace_bytes=lambda P, B, F: 1024)
+                                     rgbd_dv_render_workspace_bytes=lambda P, B, F: 1024,
+                                     rgbd_dv_workspace_bytes=lambda P: 1024,
+                                     rgbd_dv_project_workspace_bytes=lambda P, B, F: 1024)
+
+    def _dvp(self, P):
+        K = np.array([[P.fx, 0, P.cx, 0], [0, P.fy, P.cy, 0], [0, 0, 1, 0], [0, 0, 0, 1.0]])
+        return self.oracle.dv_params(P.W, P.H, P.D, P.G, K, P.voxel_size, P.near_plane)
 
     def _common(self, a):
         img, img_rot, M, c, Mi, ci, B, C, H, W, opts = a[:11]
@@ -168,6 +174,49 @@ class OracleBackedLib:
                 outs = self.oracle.dv_render_bwd(*args, _view(a[11], (B, F, P.H, P.W)), _view(a[12], (B, P.H, P.W)), g_fg)
                 for ptr, o in zip(a[14:19], outs):
                     _view(ptr, o.shape)[...] = o
+        elif name == "rgbd_warp_fwd":
+            z, M, cv, B, H, W, out, _ = a
+            _view(out, (B, H * W, 3))[...] = self.oracle.warp_fwd(_view(z, (B, 1, H * W)), _view(M, (B, 9)), _view(cv, (B, 3)), H, W)
+        elif name == "rgbd_warp_bwd":
+            g, M, B, H, W, gz, _ = a
+            _view(gz, (B, 1, H * W))[...] = self.oracle.warp_bwd(_view(g, (B, H * W, 3)), _view(M, (B, 9)), H, W)
+        elif name == "rgbd_bilinear_fwd":
+            img, zp, B, C, H, W, warped, mask, _ = a
+            w, m = self.oracle.bilinear_fwd(_view(img, (B, C, H, W)), _view(zp, (B, H * W, 3)))
+            _view(warped, (B * H * W, C))[...] = w
+            _view(mask, (B * H * W,), ctypes.c_uint8)[...] = m
+        elif name == "rgbd_bilinear_bwd":
+            img, zp, g, B, C, H, W, g_img, g_zp, _ = a
+            gi, gz = self.oracle.bilinear_bwd(_view(img, (B, C, H, W)), _view(zp, (B, H * W, 3)), _view(g, (B * H * W, C)))
+            _view(g_img, (B, C, H, W))[...] = gi
+            _view(g_zp, (B, H * W, 3))[...] = gz
+        elif name == "rgbd_dv_compute_proj_idcs":
+            P, cam, lin, vc, M, ws, wsb, _ = a
+            P = P._obj
+            n = P.W * P.H * P.D
+            r = self.oracle.dv_compute_proj_idcs(self._dvp(P), _view(cam, (4, 4)))
+            M._obj.value = 0 if r is None else r[0].size
+            if r is not None:
+                _view(lin, (n,), ctypes.c_int32)[:r[0].size] = r[0]
+                _view(vc, (3, n))[:, :r[0].size] = r[1]
+        elif name in ("rgbd_dv_trilinear_fwd", "rgbd_dv_trilinear_bwd"):
+            src, lin, vc, ld, M, F, P, dst, _ = a
+            P = P._obj
+            n, G = P.W * P.H * P.D, P.G
+            li = _view(lin, (M,), ctypes.c_int32)
+            v = _view(vc, (3, ld))[:, :M]
+            if name.endswith("fwd"):
+                _view(dst, (F, n))[...] = self.oracle.dv_trilinear_fwd(_view(src, (F, G, G, G)), li, v, P).reshape(F, n)
+            else:
+                _view(dst, (F, G, G, G))[...] = self.oracle.dv_trilinear_bwd(_view(src, (F, n)), li, v, P)
+        elif name in ("rgbd_dv_project_fwd", "rgbd_dv_project_bwd"):
+            P, src, cam, B, F, dst, ws, wsb, _ = a
+            P0 = self._dvp(P._obj)
+            G, sh = P0.G, (B, F, P0.D, P0.H, P0.W)
+            if name.endswith("fwd"):
+                _view(dst, sh)[...] = self.oracle.dv_project_fwd(P0, _view(src, (B, F, G, G, G)), _view(cam, (B, 4, 4)))
+            else:
+                _view(dst, (B, F, G, G, G))[...] = self.oracle.dv_project_bwd(P0, _view(src, sh), _view(cam, (B, 4, 4)))
         else:
             raise AssertionError("unexpected C-ABI call " + name)
 
@@ -248,3 +297,115 @@ def test_chainer_render_node(nodes, oracle_mod, name):
     for v, key in zip(ins, ("g_grid", "g_W1", "g_b1", "g_W2", "g_b2")):
         assert rel(np.asarray(v.grad).reshape(g[key].shape), g[key]) <= 1e-5, key
     assert lib.calls == ["rgbd_dv_render_fwd", "rgbd_dv_render_bwd"]
+
+
+# ------------------------------------------------------------------ the rest of the reference's call surface
+def test_chainer_module_imports_without_torch():
+    """the Chainer + CuPy deployment has no torch: importing the nodes must not pull it in"""
+    import subprocess
+    code = ("import sys, importlib.abc\n"
+            "class Block(importlib.abc.MetaPathFinder):\n"
+            "    def find_spec(self, name, path, target=None):\n"
+            "        if name == 'torch' or name.startswith('torch.'): raise ImportError('torch is blocked')\n"
+            "sys.meta_path.insert(0, Block())\n"
+            "import rgbd_gan_b200.chainer_nodes as cn\n"
+            "assert 'torch' not in sys.modules\n"
+            "print(sorted(cn.__all__))\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                         cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert out.returncode == 0, out.stderr
+    assert "LossFuncRotate" in out.stdout and "interpolate_trilinear" in out.stdout
+
+
+def test_chainer_debug_tuple_and_free_functions(nodes, oracle_mod):
+    """debug=True (:100-102) and the free functions warp / inv_warp / bilinear (:171-228) against the golden intermediates,
+    gradients of bilinear through the shim's reverse walk"""
+    g = load_golden("loss_cfg0_l1_occ")
+    o = case_options(g)
+    B, S = o["B"], o["S"]
+    N = B * S * S
+    lib = OracleBackedLib(oracle_mod)
+    xp = FakeXP()
+    f = nodes.LossFuncRotate(xp, lambda_geometric=o["lam"], lib=lib)
+    V = chainer_shim.Variable
+    img, img_rot = V(_wrap(g["x"][:B])), V(_wrap(g["x"][B:]))
+    warped, not_out, new_zp, warped_rot, not_out_rot, new_zp_rot = f(img, g["cam"][:B], img_rot, g["cam"][B:], debug=True)
+    np.testing.assert_array_equal(np.asarray(new_zp.array), g["new_zp_cat"][:B])
+    np.testing.assert_array_equal(np.asarray(new_zp_rot.array), g["new_zp_cat"][B:])
+    np.testing.assert_array_equal(np.asarray(not_out), g["not_out"])
+    np.testing.assert_array_equal(np.asarray(not_out_rot), g["not_out_rot"])
+    np.testing.assert_array_equal(np.asarray(warped.array), g["warped"])
+    np.testing.assert_array_equal(np.asarray(warped_rot.array), g["warped_rot"])
+    assert lib.calls == ["rgbd_warp_fwd", "rgbd_warp_fwd", "rgbd_bilinear_fwd", "rgbd_bilinear_fwd"]
+    # free functions with the reference's argument lists
+    from oracle import numpy_port as npp
+    port = npp.LossFuncRotateNP(lambda_geometric=o["lam"])
+    port.init_params(S)
+    th, thr = g["cam"][:B], g["cam"][B:]
+    R = np.matmul(thr[:, :3, :3].transpose(0, 2, 1), th[:, :3, :3]).astype("float32")
+    t = np.matmul(th[:, :3, :3].transpose(0, 2, 1), thr[:, :3, -1:] - th[:, :3, -1:]).astype("float32")
+    z = V(_wrap(g["x"][:B, -1:].reshape(B, 1, -1)))
+    zp = nodes.warp(port.K, port.inv_K, R, t, z, port.p, xp=xp, lib=lib)
+    np.testing.assert_array_equal(np.asarray(zp.array), g["new_zp_cat"][:B])
+    z_rot = V(_wrap(g["x"][B:, -1:].reshape(B, 1, -1)))
+    zpr = nodes.inv_warp(port.K, port.inv_K, R.transpose(0, 2, 1), t, z_rot, port.p, xp=xp, lib=lib)
+    np.testing.assert_array_equal(np.asarray(zpr.array), g["new_zp_cat"][B:])
+    w, m = nodes.bilinear(img_rot, zp, xp=xp, lib=lib)
+    np.testing.assert_array_equal(np.asarray(m), g["not_out"])
+    # gradient flows into the sampled image and, through new_zp, into the depth of the source image
+    gw = np.random.default_rng(0).normal(size=w.shape).astype(np.float32)
+    F_ = chainer_shim.functions
+    F_.sum(w * gw).backward()
+    ref_gi, ref_gzp = oracle_mod.bilinear_bwd(g["x"][B:], g["new_zp_cat"][:B], gw)
+    assert_grad_close(np.asarray(img_rot.grad), ref_gi)
+    M, _ = __import__("rgbd_gan_b200.host_math", fromlist=["x"]).warp_constants(port.K, port.inv_K, R, t, False)
+    assert_grad_close(np.asarray(z.grad).reshape(B, 1, -1), oracle_mod.warp_bwd(ref_gzp, M, S, S))
+
+
+@pytest.mark.parametrize("name", ["dv_g16_f3"])
+def test_chainer_projection_surface(nodes, oracle_mod, name):
+    """ProjectionHelper.compute_proj_idcs (projection.py:48-105), interpolate_trilinear (deepvoxel.py:388-428) and the
+    fused batch projection, values and gradients against the reference's golden vectors"""
+    g = load_golden(name)
+    G, img, F, D = int(g["G"]), int(g["img"]), int(g["F"]), int(g["D"])
+    lib = OracleBackedLib(oracle_mod)
+    xp = FakeXP()
+    h = nodes.ProjectionHelper(g["intrinsic"], g["intrinsic"], [img, img], [img, img], 0., 1., [G] * 3,
+                               float(g["voxel_size"]), float(g["near_plane"]), D, verbose=False, xp=xp, lib=lib)
+    V = chainer_shim.Variable
+    F_ = chainer_shim.functions
+    for i in range(g["cam"].shape[0]):
+        lin, vc = h.compute_proj_idcs(g["cam"][i])
+        np.testing.assert_array_equal(np.asarray(lin), g["lin_ind_%d" % i])
+        np.testing.assert_array_equal(np.asarray(vc), g["voxel_coords_%d" % i])
+        grid = V(_wrap(g["grid"][i:i + 1]))
+        out = nodes.interpolate_trilinear(grid, lin, vc, [img, img], D, xp=xp, lib=lib)
+        assert out.shape == (1, F, D, img, img)
+        np.testing.assert_array_equal(np.asarray(out.array), g["frustum_%d" % i])
+        F_.sum(out * g["g_out"][i:i + 1]).backward()
+        assert_grad_close(np.asarray(grid.grad), g["g_grid_%d" % i])
+    far = g["cam"][0].copy()
+    far[:3, 3] += 100.0
+    assert h.compute_proj_idcs(far) is None                       # "error: nothing in frustum bounds" (:98-100)
+    grid = V(_wrap(g["grid"]))
+    fr = h.project(grid, g["cam"])
+    F_.sum(fr * g["g_out"]).backward()
+    for i in range(g["cam"].shape[0]):
+        np.testing.assert_array_equal(np.asarray(fr.array)[i], g["frustum_%d" % i][0])
+        assert_grad_close(np.asarray(grid.grad)[i], g["g_grid_%d" % i][0])
+    assert lib.calls.count("rgbd_dv_project_fwd") == 1 and lib.calls.count("rgbd_dv_project_bwd") == 1
+
+
+def test_chainer_node_returns_only_requested_gradients(nodes, oracle_mod):
+    """FunctionNode.backward contract: one gradient per target_input_index (only img_rot requires grad here)"""
+    g = load_golden("loss_cfg0_l1_occ")
+    o = case_options(g)
+    B = o["B"]
+    lib = OracleBackedLib(oracle_mod)
+    f = nodes.LossFuncRotate(FakeXP(), lambda_geometric=o["lam"], lib=lib)
+    V = chainer_shim.Variable
+    img, img_rot = V(_wrap(g["x"][:B]), requires_grad=False), V(_wrap(g["x"][B:]))
+    loss, _ = f(img, g["cam"][:B], img_rot, g["cam"][B:], occlusion_aware=o["occ"])
+    (loss * o["gy"]).backward()
+    assert img.grad is None
+    assert_grad_close(np.asarray(img_rot.grad), g["g_img_rot"])

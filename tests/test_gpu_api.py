@@ -191,3 +191,34 @@ def test_depth_hinge_through_python_mirror(fuse):
     assert abs(loss.item() - float(g["total"])) <= 1e-5 * abs(float(g["total"]))
     assert_grad_close(img.grad.cpu().numpy(), g["g_img"])
     assert_grad_close(img_rot.grad.cpu().numpy(), g["g_img_rot"])
+
+
+def test_peer_exchange_wait_is_bounded(monkeypatch):
+    """a rank whose peers never show up (dead process, different call sequence) must get an error, not a hung GPU:
+    world-2 comm on ONE GPU whose second mailbox is a local buffer nobody writes (rgbd_debug_peer_comm_loopback)"""
+    import ctypes
+    import time
+    from gpu_util import Consistency
+    from oracle import numpy_port as npp
+    from rgbd_gan_b200 import _lib
+    monkeypatch.setenv("RGBD_B200_PEER_TIMEOUT_MS", "50")
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    ipc = ctypes.create_string_buffer(64)
+    _lib.check(lib.rgbd_peer_comm_create(0, 2, ctypes.byref(h), ipc), "create")
+    _lib.check(lib.rgbd_debug_peer_comm_loopback(h), "loopback")
+    g = load_golden("loss_s64_l1_noocc")
+    o = case_options(g)
+    port = npp.LossFuncRotateNP(lambda_geometric=o["lam"])
+    port.init_params(o["S"])
+    drv = Consistency(g["x"], g["cam"], o["B"], port.K, port.inv_K, lam=o["lam"], occ=o["occ"], n_pairs_global=2 * o["B"])
+    drv.opts.peer_comm = h.value
+    t0 = time.perf_counter()
+    parts, gi, gr = drv.fwd_bwd(gy=o["gy"])                       # returns: the wait gives up after 50 ms
+    status = ctypes.c_int(-1)
+    _lib.check(lib.rgbd_peer_comm_status(h, None, ctypes.byref(status)), "status")
+    assert status.value == 1 and time.perf_counter() - t0 < 5.0
+    assert_grad_close(gi * 2, g["g_img"])                          # gradients never depend on the exchange
+    drv.opts.peer_comm = None
+    torch.cuda.synchronize()
+    lib.rgbd_peer_comm_destroy(h)
