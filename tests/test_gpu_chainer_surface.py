@@ -55,7 +55,7 @@ class TArr:
     def reshape(self, *shape):
         if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
             shape = tuple(shape[0])
-        return TArr(self.t.reshape(*shape))
+        return TArr(self.t.reshape(tuple(shape)))
 
     def __getitem__(self, k):
         return TArr(self.t[k])
