@@ -109,6 +109,15 @@ RGBD_API int rgbd_consistency_uses_sweep(int B, int C, int H, int W);
  * raises a sticky flag instead of hanging the GPU.  Synchronises `stream`; *status_host = 0 ok, 1 timed out. */
 RGBD_API int rgbd_consistency_status(const void *workspace, void *stream, int *status_host);
 
+/* Test aid: evaluates the kernels' shared-reciprocal division (two quotients by one denominator in [1e-4, 1e4], the
+ * range of F.clip(zp2, 1e-4, 10000), loss_functions.py:199) on n pseudo-random (a0, a1, b) and compares it bit for bit
+ * with IEEE division (__fdiv_rn): counts_dev[0] = mismatches of the row-sweep kernel's variant incl. its fallback rule,
+ * [1] = mismatches of the three-kernel chain's variant, [2] = samples that took the fallback.  Numerator exponents are
+ * uniform in [e_lo, e_hi] (e.g. -70..70 covers both sides of the 2^-60 / 2^60 fallback thresholds); exact zeros and the
+ * exact denominator bounds are mixed in. */
+RGBD_API int rgbd_debug_div2(unsigned long long n, unsigned seed, int e_lo, int e_hi, unsigned long long *counts_dev,
+                             void *stream);
+
 /* Test aid (no GPU needed): the ticket order of one launch of the pipeline kernel for a chunk of Bc pairs of H x W
  * images: tickets[3t..3t+2] = (role, pair, tile) with role 0 none, 1 stage-in, 2 main, 3 stage-out, 4 loss finalize;
  * *total_out = number of tickets.  tests/test_host_logic.py checks that every tile appears once and that every

@@ -532,4 +532,45 @@ k_sweep_fixup(const SweepArgs a, int nlists, const FinalizeArgs fin)
     }
 }
 
+// ---- test aid: the shared-reciprocal divisions against IEEE division on the device (tests/test_gpu_sweep.py)
+__device__ __forceinline__ unsigned sw_hash(unsigned x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+// numerators: sign * 2^e * mantissa with e uniform in [e_lo, e_hi]; denominators: log-uniform in [1e-4, 1e4] (the range
+// of clip(q2, 1e-4, 1e4), :199) plus the exact bounds.  counts[0] = mismatches of div_fast + its fallback rule (sweep
+// kernel), counts[1] = mismatches of div2_rn (three-kernel chain), counts[2] = samples that took a fallback.
+__global__ void __launch_bounds__(kThreads)
+k_debug_div2(unsigned long long n, unsigned seed, int e_lo, int e_hi, unsigned long long *counts)
+{
+    unsigned long long bad_fast = 0, bad_chain = 0, slow = 0;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * kThreads + threadIdx.x; k < n; k += (unsigned long long)gridDim.x * kThreads) {
+        const unsigned h0 = sw_hash((unsigned)k * 3u + seed), h1 = sw_hash((unsigned)k * 3u + 1u + seed),
+                       h2 = sw_hash((unsigned)k * 3u + 2u + seed + (unsigned)(k >> 32));
+        auto num = [&](unsigned h) {
+            const int e = e_lo + (int)((h >> 24) % (unsigned)(e_hi - e_lo + 1));
+            const float m = __uint_as_float(0x3f800000u | (h & 0x7fffffu));            // [1, 2)
+            const float v = ldexpf(m, e);
+            return (h & 0x800000u) ? -v : v;
+        };
+        const float a0 = (k % 1021 == 0) ? 0.0f : num(h0), a1 = num(h1);
+        float b = __expf(-9.2103404f + 18.420681f * ((h2 >> 8) * (1.0f / 16777216.0f)));   // log-uniform [1e-4, 1e4]
+        b = fminf(fmaxf(b, 1e-4f), 10000.0f);
+        if (k % 4099 == 0) b = (k & 1) ? 1e-4f : 10000.0f;
+        const float r0 = __fdiv_rn(a0, b), r1 = __fdiv_rn(a1, b);
+        float q0, q1, rinv;
+        bool bad;
+        div_fast(a0, a1, b, q0, q1, rinv, bad);
+        if (bad) { q0 = __fdiv_rn(a0, b); q1 = __fdiv_rn(a1, b); ++slow; }
+        if (__float_as_uint(q0) != __float_as_uint(r0) || __float_as_uint(q1) != __float_as_uint(r1)) ++bad_fast;
+        float c0, c1, cr;
+        div2_rn(a0, a1, b, c0, c1, cr);
+        if (__float_as_uint(c0) != __float_as_uint(r0) || __float_as_uint(c1) != __float_as_uint(r1)) ++bad_chain;
+    }
+    if (bad_fast) atomicAdd(counts, bad_fast);
+    if (bad_chain) atomicAdd(counts + 1, bad_chain);
+    if (slow) atomicAdd(counts + 2, slow);
+}
+
 }  // namespace rgbd

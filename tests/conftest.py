@@ -59,14 +59,17 @@ def rel_max(a, b):
                  max(float(np.abs(b).max()), 1e-30))
 
 
-def assert_grad_close(got, ref, tol=1e-5, elem_rtol=1e-3):
-    """Gradient tolerance of the north star: |a-b| <= 1e-5 * max|ref| for every element (error
-    relative to the tensor's max-norm).  Many entries are exactly 0 (masked / occluded pixels) and
-    the depth-channel entries are sums with heavy cancellation, so a per-element relative error
-    is not meaningful at 1e-5: two op-by-op fp32 evaluations of the SAME reference graph that only
-    differ in accumulation order already disagree by ~1e-4 on entries of size 1e-3*max (measured:
-    oracle/numpy_port.py vs the golden vectors).  As a structural sanity check, entries larger than
-    1e-3*max must still agree to `elem_rtol`."""
+def assert_grad_close(got, ref, tol=1e-5, elem_rtol=5e-4):
+    """Gradient tolerance of the north star: |a-b| <= 1e-5 * max|ref| for every element (error relative to the tensor's
+    max-norm; measured worst case over every golden case and a 64-pair full-size run, both C == 4 paths: 6.8e-7,
+    profiles/r02_grad_tolerance.json).
+
+    SURVEY 8(c) adds an element-wise check for entries larger than 1e-3 * max|ref|.  Many entries are exactly 0 (masked /
+    occluded pixels) and the depth-channel entries are sums with heavy cancellation (M^T gq . (x, y, 1) with x, y up to
+    127), so two fp32 evaluations of the SAME reference graph that differ only in summation order already disagree at the
+    1e-4 level on such entries.  The bound is set from data, not by argument: tools/grad_tolerance.py measures the
+    element-wise relative error of the CUDA paths against the golden vectors / the C oracle (worst entry 2.1e-4, 99.9th
+    percentile <= 3e-5, median ~1e-7); `elem_rtol` is about 2x the measured worst case."""
     got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
     assert got.shape == ref.shape
     scale = np.abs(ref).max()

@@ -222,3 +222,38 @@ def test_peer_exchange_wait_is_bounded(monkeypatch):
     drv.opts.peer_comm = None
     torch.cuda.synchronize()
     lib.rgbd_peer_comm_destroy(h)
+
+
+def test_occupancy_net_loss_and_calc_real_pos_smoke():
+    """LossFuncRotate.calc_real_pos (:148-158) against the NumPy expression and occupancy_net_loss (:160-168) end to
+    end with a stand-in occupancy network: finite scalar, gradient reaches the network and the depth"""
+    from rgbd_gan_b200.loss_functions import LossFuncRotate
+    g = load_golden("loss_s64_l1_noocc")
+    o = case_options(g)
+    B, S = o["B"], o["S"]
+    x = torch.from_numpy(g["x"]).to(DEV)
+    f = LossFuncRotate(None, lambda_geometric=o["lam"])
+    f.init_params(None, size=S)
+    theta = g["cam"][:B]
+    out = f.calc_real_pos(x[:B], theta)
+    z = g["x"][:B, -1:].reshape(B, 1, -1)
+    ref = np.matmul(np.matmul(theta[:, :3, :3], f.inv_K), z * f.p) + theta[:, :3, -1:]
+    assert out.shape == (B, 6, S * S)
+    np.testing.assert_allclose(out[:, 3:].cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    np.testing.assert_array_equal(out[:, :3].cpu().numpy(), g["x"][:B, :3].reshape(B, 3, -1))
+
+    class Occ(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.randn(3, device=DEV) * 0.1)
+
+        def forward(self, zlat, pos):                                  # pos (B,3,HW) -> logits (B*HW,1)
+            return (pos * self.w[None, :, None]).sum(1).reshape(-1, 1) + zlat.mean()
+
+    net = Occ()
+    depth = x[:B, -1:].clone().requires_grad_(True)
+    loss = f.occupancy_net_loss(net, depth, theta, torch.randn(B, 8, device=DEV))
+    assert loss.dim() == 0 and torch.isfinite(loss)
+    loss.backward()
+    assert torch.isfinite(net.w.grad).all() and float(net.w.grad.abs().sum()) > 0
+    assert depth.grad is not None and torch.isfinite(depth.grad).all()

@@ -131,3 +131,68 @@ def test_sweep_depth_hinge(name, ctas, monkeypatch):
     assert abs(parts[6] - float(g["total"])) <= 1e-5 * abs(float(g["total"]))
     assert_grad_close(gi, g["g_img"])
     assert_grad_close(gr, g["g_img_rot"])
+
+
+@pytest.mark.parametrize("e_lo,e_hi", [(-20, 20), (-70, 70), (-126, 126)])
+def test_div2_matches_ieee_division(e_lo, e_hi):
+    """the shared-reciprocal division that feeds the truncated pixel indices (both kernels' variants) against __fdiv_rn on
+    1e8 pseudo-random (a0, a1, b in [1e-4, 1e4]) per exponent range, incl. the 2^-60 / 2^60 fallbacks: bit-equal"""
+    import ctypes
+    from rgbd_gan_b200 import _lib
+    counts = torch.zeros(3, dtype=torch.int64, device="cuda:0")
+    _lib.call("rgbd_debug_div2", ctypes.c_ulonglong(100_000_000), 12345 + e_hi, e_lo, e_hi, ctypes.c_void_p(counts.data_ptr()),
+              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    c = counts.cpu().numpy()
+    assert c[0] == 0 and c[1] == 0, c
+    if e_hi >= 70:
+        assert c[2] > 0            # the fallback was exercised
+
+
+def test_feature_space_shape_c257_against_oracle(oracle_mod):
+    """SURVEY 8(f) rank 3 at its production shape (updater.py:345-354): C = 256 features + 1 depth at 32x32, norm l2 --
+    8 lane iterations and an odd row stride in the warp-per-pixel kernels"""
+    from gpu_util import Consistency
+    from oracle import numpy_port as npp
+    B, C, S = 6, 257, 32
+    rng = np.random.default_rng(4)
+    _, cam = npp.synthetic_batch(B, S, depth="rough", seed=4)
+    x = rng.uniform(-1, 1, size=(2 * B, C, S, S)).astype(np.float32)
+    x[:, -1] = rng.uniform(0.7, 1.5, size=(2 * B, S, S))
+    port = npp.LossFuncRotateNP(norm="l2", lambda_geometric=3)
+    port.init_params(S)
+    drv = Consistency(x, cam, B, port.K, port.inv_K, norm="l2", lam=3.0, occ=True)
+    M, c, Mi, ci = drv.host_poses
+    ref_parts, d = oracle_mod.consistency_fwd(x[:B], x[B:], M, c, Mi, ci, norm=2, occlusion=True, debug=True)
+    ref_gi, ref_gr = oracle_mod.consistency_bwd(x[:B], x[B:], M, c, Mi, ci, norm=2, occlusion=True, lambda_geometric=3, gy=2.0)
+    parts, zp, masks = drv.fwd()
+    np.testing.assert_array_equal(zp, d["new_zp"])
+    np.testing.assert_array_equal(masks[0], d["mask"])
+    np.testing.assert_array_equal(masks[1], d["occ"])
+    np.testing.assert_allclose(parts[:4], ref_parts, rtol=1e-5)
+    parts2, gi, gr = drv.fwd_bwd(gy=2.0)
+    np.testing.assert_allclose(parts2[:4], ref_parts, rtol=1e-5)
+    assert_grad_close(gi, ref_gi)
+    assert_grad_close(gr, ref_gr)
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_configs2_car_poses_full_size(mode, oracle_mod, monkeypatch):
+    """BASELINE.json configs[2] (dcgan_shapenet_car.yml): 64 pairs at 128x128, car pose ranges (yaw +-pi), lambda_geometric 1,
+    occlusion on, through both C == 4 paths"""
+    from oracle import numpy_port as npp
+    monkeypatch.setenv("RGBD_B200_SWEEP", mode)
+    B, S = 64, 128
+    x, cam = npp.synthetic_batch(B, S, depth="rough", ranges=npp.CAR_RANGES, seed=21)
+    port = npp.LossFuncRotateNP(lambda_geometric=1)
+    port.init_params(S)
+    from gpu_util import Consistency
+    drv = Consistency(x, cam, B, port.K, port.inv_K, lam=1.0, occ=True)
+    M, c, Mi, ci = drv.host_poses
+    ref_parts = oracle_mod.consistency_fwd(x[:B], x[B:], M, c, Mi, ci, norm=1, occlusion=True)
+    ref_gi, ref_gr = oracle_mod.consistency_bwd(x[:B], x[B:], M, c, Mi, ci, norm=1, occlusion=True, lambda_geometric=1, gy=2.0)
+    parts, gi, gr = drv.fwd_bwd(gy=2.0)
+    np.testing.assert_allclose(parts[:4], ref_parts, rtol=1e-5)
+    lam = np.float32(1.0)
+    assert parts[4] == np.float32((parts[0] + parts[1]) + (parts[2] * lam + parts[3] * lam))
+    assert_grad_close(gi, ref_gi)
+    assert_grad_close(gr, ref_gr)
