@@ -194,6 +194,13 @@ RGBD_API int rgbd_debug_peer_comm_loopback(void *comm);
 
 /* warp (:171-175) / inv_warp (:178-182): new_zp[b,n,:] = M[b] (z[b,n] * p[:,n]) - cv[b]
  * with p = (col,row,1) (:59-61).  z: (B,HW); new_zp: (B,HW,3).  inv_warp passes cv = -(K t). */
+/* ---- "next" row: the generators' depth head, net.py:294-299 / :756-761 -----------------------
+ *   depth = 1 / (F.softplus(h[:, -1:]) + 1e-4);  h = F.concat([h[:, :3], depth])
+ * h, out, g_out, g_h: (B,C,H,W); the last channel is transformed, the others are copied.  out may alias h and g_h may
+ * alias g_out (in place: only the depth plane is touched).  fp32, within 1e-5 of the reference expression. */
+RGBD_API int rgbd_depth_head_fwd(const float *h, int B, int C, int H, int W, float *out, void *stream);
+RGBD_API int rgbd_depth_head_bwd(const float *h, const float *g_out, int B, int C, int H, int W, float *g_h, void *stream);
+
 RGBD_API int rgbd_warp_fwd(const float *z, const float *M, const float *cv, int B, int H, int W,
                   float *new_zp, void *stream);
 /* g_z (B,HW) = sum_k (M[b]^T g_new_zp[b,n,:])_k p_k[n]   (autograd of F.matmul and z * p) */

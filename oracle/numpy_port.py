@@ -299,6 +299,24 @@ def depth_hinge(x_fake, depth_min, lambda_depth, gy=None):
 
 
 # ---------------------------------------------------------------------- DeepVoxels projection
+def depth_head_fwd(h):
+    """net.py:294-299 / :756-761 op by op (Chainer's softplus forward_cpu, AddConstant, DivFromConstant, Concat)"""
+    h = np.asarray(h, f32)
+    x = h[:, -1:]
+    sp = (np.fmax(x, 0) + np.log1p(np.exp(-np.fabs(x)))).astype(f32)
+    return np.concatenate([h[:, :-1], (f32(1.0) / (sp + f32(1e-4))).astype(f32)], axis=1)
+
+
+def depth_head_bwd(h, g_out):
+    h, g_out = np.asarray(h, f32), np.asarray(g_out, f32)
+    x = h[:, -1:]
+    sp = (np.fmax(x, 0) + np.log1p(np.exp(-np.fabs(x)))).astype(f32)
+    v = sp + f32(1e-4)
+    g_v = (-f32(1.0) * g_out[:, -1:] / (v ** 2)).astype(f32)                  # DivFromConstant.backward
+    g_x = ((1 - 1 / (1 + np.exp(x))) * g_v).astype(f32)                       # SoftplusGrad.forward_cpu
+    return np.concatenate([g_out[:, :-1], g_x], axis=1)
+
+
 class ProjectionHelperNP:
     """deepvoxel/projection.py:5-105 with fp32-pinned scalar semantics (Q6)."""
 

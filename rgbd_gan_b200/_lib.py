@@ -60,6 +60,8 @@ SIGNATURES = {
     "rgbd_consistency_workspace_bytes": (c_size, [c_int, c_int, c_int, c_int]),
     "rgbd_consistency_uses_sweep": (c_int, [c_int, c_int, c_int, c_int]),
     "rgbd_consistency_status": (c_int, [c_void, c_void, ctypes.POINTER(c_int)]),
+    "rgbd_depth_head_fwd": (c_int, [c_void, c_int, c_int, c_int, c_int, c_void, c_void]),
+    "rgbd_depth_head_bwd": (c_int, [c_void, c_void, c_int, c_int, c_int, c_int, c_void, c_void]),
     "rgbd_debug_div2": (c_int, [ctypes.c_ulonglong, ctypes.c_uint, c_int, c_int, c_void, c_void]),
     "rgbd_debug_mega_schedule": (c_int, [c_int] * 7 + [ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int)]),
     "rgbd_consistency_fwd": (c_int, [c_void] * 6 + [c_int] * 4 + [ctypes.POINTER(LossOpts), c_void, c_void, c_void,

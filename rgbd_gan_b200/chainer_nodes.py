@@ -315,6 +315,37 @@ class LossFuncRotate:
         return F.sigmoid_cross_entropy(occupancy_field, label)
 
 
+class DepthHead(FunctionNode):
+    """"next" row: the generators' depth head (net.py:294-299, :756-761) as one node:
+    h (B,C,H,W) -> concat([h[:, :-1], 1 / (softplus(h[:, -1:]) + 1e-4)])"""
+
+    def __init__(self, xp=None, lib=None):
+        self.xp = xp if xp is not None else cupy
+        self.lib = lib if lib is not None else _lib
+
+    def forward(self, inputs):
+        xp = self.xp
+        h = xp.ascontiguousarray(inputs[0], dtype="float32")
+        self.retain_inputs((0,))
+        B, C, H, W = h.shape
+        out = xp.empty_like(h)
+        self.lib.call("rgbd_depth_head_fwd", _ptr(h), B, C, H, W, _ptr(out), _stream(xp))
+        return out,
+
+    def backward(self, target_input_indexes, grad_outputs):
+        xp = self.xp
+        h = xp.ascontiguousarray(_arr(self.get_retained_inputs()[0]), dtype="float32")
+        B, C, H, W = h.shape
+        g = _f32c(xp, grad_outputs[0])
+        g_h = xp.empty_like(h)
+        self.lib.call("rgbd_depth_head_bwd", _ptr(h), _ptr(g), B, C, H, W, _ptr(g_h), _stream(xp))
+        return _as_var(g_h),
+
+
+def depth_head(h, xp=None, lib=None):
+    return DepthHead(xp=_xp_of(h, xp), lib=lib).apply((h,))[0]
+
+
 # ------------------------------------------------------------------------------------------------- DeepVoxels
 class Project(FunctionNode):
     """the generator's per-sample loops (deepvoxels_generator.py:287-299 -> deepvoxel.py:879-884: compute_proj_idcs +
@@ -523,4 +554,5 @@ class RenderAccumulative(FunctionNode):
 
 
 __all__ = ["LossFuncRotate", "warp", "inv_warp", "bilinear", "ProjectionHelper", "interpolate_trilinear",
-           "ConsistencyLoss", "Warp", "Bilinear", "Project", "Trilinear", "RenderAccumulative", "HAVE_CHAINER"]
+           "ConsistencyLoss", "Warp", "Bilinear", "Project", "Trilinear", "RenderAccumulative", "DepthHead", "depth_head",
+           "HAVE_CHAINER"]

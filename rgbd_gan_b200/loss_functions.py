@@ -354,4 +354,29 @@ def bilinear(img, zp):
     return _BilinearFn.apply(img, zp)
 
 
-__all__ = ["LossFuncRotate", "warp", "inv_warp", "bilinear", "pose_algebra", "combine_loss_parts"]
+class _DepthHeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h):
+        B, C, H, W = h.shape
+        out = torch.empty_like(h)
+        _lib.call("rgbd_depth_head_fwd", _ptr(h), B, C, H, W, _ptr(out), _stream())
+        ctx.save_for_backward(h)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        h, = ctx.saved_tensors
+        B, C, H, W = h.shape
+        g_out = g_out.to(torch.float32).contiguous()
+        g_h = torch.empty_like(h)
+        _lib.call("rgbd_depth_head_bwd", _ptr(h), _ptr(g_out), B, C, H, W, _ptr(g_h), _stream())
+        return g_h
+
+
+def depth_head(h):
+    """"next" row: the generators' depth head (net.py:294-299, :756-761) as one kernel --
+    F.concat([h[:, :-1], 1 / (F.softplus(h[:, -1:]) + 1e-4)]); differentiable in h"""
+    return _DepthHeadFn.apply(_dev_f32(h, "h"))
+
+
+__all__ = ["LossFuncRotate", "warp", "inv_warp", "bilinear", "pose_algebra", "combine_loss_parts", "depth_head"]

@@ -643,7 +643,27 @@ class LeakyReLU(FunctionNode):
         return g,
 
 
+class Softplus(FunctionNode):
+    """chainer.functions.softplus (activation/softplus.py): forward_cpu (fmax(bx, 0) + log1p(exp(-fabs(bx)))) / beta,
+    backward (SoftplusGrad.forward_cpu) gy * (1 - 1 / (1 + exp(beta * x)))"""
+    def __init__(self, beta=1.0):
+        self.beta = float(beta)
+        self.beta_inv = float(1.0 / beta)
+
+    def forward(self, x):
+        self.x = x[0]
+        bx = self.beta * x[0]
+        y = (numpy.fmax(bx, 0) + numpy.log1p(numpy.exp(-numpy.fabs(bx)))) * self.beta_inv
+        return _force_array(y.astype(x[0].dtype)),
+
+    def backward(self, idx, gy):
+        x = self.x
+        gx = (1 - 1 / (1 + numpy.exp(self.beta * x))) * _arr(gy[0])
+        return _force_array(gx.astype(x.dtype)),
+
+
 functions = types.ModuleType("chainer.functions")
+functions.softplus = lambda x, beta=1.0: Softplus(beta).apply((x,))[0]
 functions.cumsum = lambda x, axis=None: Cumsum(axis).apply((x,))[0]
 functions.sum = lambda x, axis=None, keepdims=False: Sum(axis, keepdims).apply((x,))[0]
 functions.sigmoid = lambda x: Sigmoid().apply((x,))[0]

@@ -158,6 +158,24 @@ def hinge_case(lf, get_cam, Prior, name, seed, B, S, depth, pose, depth_min, lam
     print("%-22s loss_rotate=%.9g hinge=%.9g" % (name, float(loss_rotate.array), float(hinge.array)))
 
 
+def depth_head_case(name, seed, B, S):
+    """next row: the generators' depth head, net.py:294-299 / :756-761 --
+        depth = 1 / (F.softplus(h[:, -1:]) + 1e-4);  h = F.concat([h[:, :3], depth])
+    the reference's expression evaluated over the shim (the surrounding Generator.forward needs the conv layers)"""
+    import chainer
+    import chainer.functions as F
+    rng = np.random.default_rng(seed)
+    h_in = (rng.normal(size=(B, 4, S, S)) * 2.0).astype(np.float32)
+    h_in[0, -1, 0, :8] = [-30.0, -12.0, -1e-3, 0.0, 1e-3, 9.0, 17.0, 40.0]         # both tails of softplus
+    h = chainer.Variable(h_in.copy())
+    depth = 1 / (F.softplus(h[:, -1:]) + 1e-4)
+    out = F.concat([h[:, :3], depth])
+    g_out = rng.normal(size=out.shape).astype(np.float32)
+    F.sum(out * g_out).backward()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), h=h_in, out=out.array, g_out=g_out, g_h=h.grad)
+    print("%-22s depth range [%.4g, %.4g]" % (name, float(out.array[:, -1].min()), float(out.array[:, -1].max())))
+
+
 def growing_case(lf, get_cam, Prior, name, seed):
     """Q9: one LossFuncRotate instance reused across sizes 32 -> 64 (K mutated in place)."""
     np.random.seed(seed)
@@ -298,6 +316,9 @@ def main():
         render_case(pj, dv, get_cam, Prior, "render_g16", 20, G=16, img=32, F=32, nsamp=2)
         render_case(pj, dv, get_cam, Prior, "render_g12_thr3", 21, G=12, img=24, F=32, nsamp=3, threshold=3)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "depthhead":  # only the depth-head case
+        depth_head_case("depth_head_s32", 30, B=3, S=32)
+        return
     c = lambda *a, **k: consistency_case(lf, get_cam, Prior, *a, **k)
     # cfg0 / cfg1 shape (BASELINE.json configs[0], [1]) at B=2
     c("loss_cfg0_l1_occ", 0, B=2, C=4, S=128, depth="rough", pose=FFHQ, occ=True, lam=3)
@@ -326,6 +347,7 @@ def main():
     # next row: DeepVoxels render tail with the accumulative occlusion module
     render_case(pj, dv, get_cam, Prior, "render_g16", 20, G=16, img=32, F=32, nsamp=2)
     render_case(pj, dv, get_cam, Prior, "render_g12_thr3", 21, G=12, img=24, F=32, nsamp=3, threshold=3)
+    depth_head_case("depth_head_s32", 30, B=3, S=32)
 
 
 if __name__ == "__main__":

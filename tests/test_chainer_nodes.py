@@ -217,6 +217,14 @@ class OracleBackedLib:
                 _view(dst, sh)[...] = self.oracle.dv_project_fwd(P0, _view(src, (B, F, G, G, G)), _view(cam, (B, 4, 4)))
             else:
                 _view(dst, (B, F, G, G, G))[...] = self.oracle.dv_project_bwd(P0, _view(src, sh), _view(cam, (B, 4, 4)))
+        elif name == "rgbd_depth_head_fwd":
+            from oracle import numpy_port as npp_
+            h, B, C, H, W, out, _ = a
+            _view(out, (B, C, H, W))[...] = npp_.depth_head_fwd(_view(h, (B, C, H, W)))
+        elif name == "rgbd_depth_head_bwd":
+            from oracle import numpy_port as npp_
+            h, g, B, C, H, W, gh, _ = a
+            _view(gh, (B, C, H, W))[...] = npp_.depth_head_bwd(_view(h, (B, C, H, W)), _view(g, (B, C, H, W)))
         else:
             raise AssertionError("unexpected C-ABI call " + name)
 
@@ -409,3 +417,16 @@ def test_chainer_node_returns_only_requested_gradients(nodes, oracle_mod):
     (loss * o["gy"]).backward()
     assert img.grad is None
     assert_grad_close(np.asarray(img_rot.grad), g["g_img_rot"])
+
+
+def test_chainer_depth_head_node(nodes, oracle_mod):
+    """next row: the generators' depth head (net.py:294-299) as a node, against the reference expression's golden"""
+    g = load_golden("depth_head_s32")
+    lib = OracleBackedLib(oracle_mod)
+    V = chainer_shim.Variable
+    h = V(_wrap(g["h"]))
+    out = nodes.depth_head(h, xp=FakeXP(), lib=lib)
+    chainer_shim.functions.sum(out * g["g_out"]).backward()
+    np.testing.assert_array_equal(np.asarray(out.array), g["out"])
+    np.testing.assert_allclose(np.asarray(h.grad), g["g_h"], rtol=1e-6, atol=1e-12)
+    assert lib.calls == ["rgbd_depth_head_fwd", "rgbd_depth_head_bwd"]

@@ -257,3 +257,26 @@ def test_occupancy_net_loss_and_calc_real_pos_smoke():
     loss.backward()
     assert torch.isfinite(net.w.grad).all() and float(net.w.grad.abs().sum()) > 0
     assert depth.grad is not None and torch.isfinite(depth.grad).all()
+
+
+def test_depth_head_next_row():
+    """depth = 1 / (softplus(h) + 1e-4) (net.py:294-299) as one kernel, values and gradient against
+    the reference expression's golden vectors, in place and with an odd plane size (scalar path)"""
+    import ctypes
+    from rgbd_gan_b200 import _lib
+    from rgbd_gan_b200.loss_functions import depth_head
+    from oracle import numpy_port as npp
+    g = load_golden("depth_head_s32")
+    h = torch.from_numpy(g["h"]).to(DEV).requires_grad_(True)
+    out = depth_head(h)
+    (out * torch.from_numpy(g["g_out"]).to(DEV)).sum().backward()
+    np.testing.assert_array_equal(out[:, :-1].detach().cpu().numpy(), g["out"][:, :-1])
+    np.testing.assert_allclose(out[:, -1].detach().cpu().numpy(), g["out"][:, -1], rtol=1e-5)
+    np.testing.assert_array_equal(h.grad[:, :-1].cpu().numpy(), g["g_h"][:, :-1])
+    np.testing.assert_allclose(h.grad[:, -1].cpu().numpy(), g["g_h"][:, -1], rtol=1e-5, atol=1e-5 * np.abs(g["g_h"][:, -1]).max() * 1e-3)
+    # in place + odd plane size (HW % 4 != 0 -> scalar path)
+    x = (np.random.default_rng(1).normal(size=(2, 4, 5, 7)) * 3).astype(np.float32)
+    t = torch.from_numpy(x).to(DEV)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.call("rgbd_depth_head_fwd", ctypes.c_void_p(t.data_ptr()), 2, 4, 5, 7, ctypes.c_void_p(t.data_ptr()), st)
+    np.testing.assert_allclose(t.cpu().numpy(), npp.depth_head_fwd(x), rtol=1e-5)

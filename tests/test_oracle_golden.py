@@ -217,3 +217,10 @@ def test_render_tail_oracle_against_reference_golden(name, oracle_mod):
     gg, gW1, gb1, gW2, gb2 = oracle_mod.dv_render_bwd(*args, g["g_novel"], g["g_depth"], g["g_fg"])
     for got, key in ((gg, "g_grid"), (gW1, "g_W1"), (gb1, "g_b1"), (gW2, "g_W2"), (gb2, "g_b2")):
         assert rel(got.reshape(g[key].shape), g[key]) <= 1e-5, key
+
+
+def test_depth_head_port_matches_reference_expression():
+    """next row: net.py:294-299 evaluated over the shim vs the op-by-op NumPy port"""
+    g = load_golden("depth_head_s32")
+    np.testing.assert_array_equal(npp.depth_head_fwd(g["h"]), g["out"])
+    np.testing.assert_allclose(npp.depth_head_bwd(g["h"], g["g_out"]), g["g_h"], rtol=1e-6, atol=1e-12)
