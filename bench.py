@@ -92,6 +92,9 @@ def run_reference(a):
         "warmup": warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(a, a.pairs),
+        "run": {"sample_pairs_per_step": procs * sample,
+                "note": "each step is a bounded sample of the workload: %d processes x %d pairs of the same "
+                        "distribution (the NumPy port's cost per pair does not depend on the batch size)" % (procs, sample)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": "oracle/numpy_port.py (op-by-op NumPy port of the Chainer CPU path; Chainer is not "
                                    "installable here), %d processes x %d pairs per step, %d steps, numpy %s"
@@ -539,11 +542,13 @@ def run_ours(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": h.world, "steps": a.steps, "warmup": a.warmup,
             "prewarm_steps": PREWARM_STEPS + 3, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(a, B), l2="input pool of %d sets x %.0f MB rotated between steps (> L2)"
-                           % (wl.pool_n, wl.bytes_per_set / 2 ** 20), cuda_graph=False,
-                           path="rgbd_consistency_fwd_bwd (one-pass fwd+bwd, upstream grad = lambda_rotate): "
-                                + ("row sweep" if wl.sweep_path else "three-kernel chain"),
-                           parallelism="dp%d (pairs sharded; 4-float loss all-reduce: %s)" % (h.world, coll)),
+            # `config` names the workload only (identical in both arms); how THIS arm ran it is under `run`
+            "config": workload_config(a, B),
+            "run": dict(l2="input pool of %d sets x %.0f MB rotated between steps (> L2)"
+                        % (wl.pool_n, wl.bytes_per_set / 2 ** 20), cuda_graph=False,
+                        path="rgbd_consistency_fwd_bwd (one-pass fwd+bwd, upstream grad = lambda_rotate): "
+                             + ("row sweep" if wl.sweep_path else "three-kernel chain"),
+                        parallelism="dp%d (pairs sharded; 4-float loss all-reduce: %s)" % (h.world, coll)),
             "two_pass": {"value": h.world * B * two_steps / (ms_two * 1e-3), "ms_per_step": ms_two / two_steps,
                          "path": "rgbd_consistency_fwd + rgbd_consistency_bwd (recompute)"},
             "e2e": e2e, "gpu_launches": int(launches_fused * a.steps),
