@@ -190,10 +190,42 @@ RGBD_API int rgbd_peer_comm_status(void *comm, void *stream, int *status_host);
  * (single process, single GPU): the next sharded loss call then exercises the bounded wait. */
 RGBD_API int rgbd_debug_peer_comm_loopback(void *comm);
 
+/* ---- "next" row: the pose pipeline on the device -------------------------------------------------
+ * CameraParamPrior.sample (train_rgbd.py:192-217) -> get_camera_matries (updater.py:26-60) -> R, inv_R, t
+ * (common/loss_functions.py:85-91) -> the constant factors of warp / inv_warp (:174, :181), one thread per pair, one
+ * launch, no host round trip.  Every product is evaluated in the rounding order of the reference's CPU path (NumPy over
+ * OpenBLAS; csrc/poses.cu lists the orders), so cam2world, M, c, Mi, ci are BIT-IDENTICAL to the host path on the
+ * golden vectors; the exception is NumPy's fp32 cos / sin, see rgbd_pose_camera_matrices.
+ *   thetas     (2B,6) fp32: rows [0,B) the first view, rows [B,2B) the rotated view (x,y,z rotation | x,y,z translation)
+ *   cam2world  (2B,4,4) fp32, same row convention
+ *   M, c, Mi, ci: (B,9) (B,3) (B,9) (B,3) as taken by rgbd_consistency_*  (ci = -(K t))
+ * K, inv_K are HOST pointers to 9 floats (LossFuncRotate.K / inv_K, :39-56).                                          */
+typedef struct {
+    double camera_param_range[6]; /* config.{x,y,z}_rotate, config.{x,y,z}_translate (train_rgbd.py:194-197) */
+    int uniform_distribution;     /* config.uniform_distribution                                             */
+} rgbd_pose_prior;
+/* CameraParamPrior.sample(2B) (:199-217) in float64 like NumPy, cast to fp32 at the end.  draws: DEVICE (B,15) float64 =
+ * per pair the reference's raw draws [uniform(-1,1) x6 | uniform(0,0.5) x6 | choice(2) x3] (replaying np.random: results
+ * bit-identical to the reference's), or NULL: Philox4x32-10 keyed by (seed, step, pair) -- same distribution, no state. */
+RGBD_API int rgbd_pose_sample(const rgbd_pose_prior *prior, int B, const double *draws, unsigned long long seed,
+                              unsigned long long step, float *thetas, void *stream);
+/* get_camera_matries(thetas, order) for n_rows independent rows.  cos_sin: optional DEVICE (n_rows,6) = cos of the three
+ * angles | sin of the three angles as the caller's array library computed them (then the result is bit-identical to
+ * the reference's); NULL: evaluated in double and rounded once (<= 1 ulp from NumPy's fp32 routines).  order: HOST int[3]
+ * or NULL = (0,1,2).                                                                                                  */
+RGBD_API int rgbd_pose_camera_matrices(const float *thetas, const float *cos_sin, int n_rows, const int *order,
+                                       float *cam2world, void *stream);
+/* loss_functions.py:85-91 + :174 / :181 from DEVICE cam2world matrices theta, theta_rot (B,4,4): what
+ * LossFuncRotate.__call__ evaluates with ~10 tiny cuBLAS launches (or, on the NumPy path, on the host).              */
+RGBD_API int rgbd_pose_algebra(const float *theta, const float *theta_rot, int B, const float *K, const float *inv_K,
+                               float *M, float *c, float *Mi, float *ci, void *stream);
+/* all three stages in one launch; thetas / cam2world may be NULL when the caller does not need them */
+RGBD_API int rgbd_pose_pipeline(const rgbd_pose_prior *prior, int B, const double *draws, unsigned long long seed,
+                                unsigned long long step, const int *order, const float *K, const float *inv_K, float *thetas,
+                                float *cam2world, float *M, float *c, float *Mi, float *ci, void *stream);
+
 /* ---- free functions of common/loss_functions.py ------------------------------------------ */
 
-/* warp (:171-175) / inv_warp (:178-182): new_zp[b,n,:] = M[b] (z[b,n] * p[:,n]) - cv[b]
- * with p = (col,row,1) (:59-61).  z: (B,HW); new_zp: (B,HW,3).  inv_warp passes cv = -(K t). */
 /* ---- "next" row: the generators' depth head, net.py:294-299 / :756-761 -----------------------
  *   depth = 1 / (F.softplus(h[:, -1:]) + 1e-4);  h = F.concat([h[:, :3], depth])
  * h, out, g_out, g_h: (B,C,H,W); the last channel is transformed, the others are copied.  out may alias h and g_h may
@@ -201,6 +233,8 @@ RGBD_API int rgbd_debug_peer_comm_loopback(void *comm);
 RGBD_API int rgbd_depth_head_fwd(const float *h, int B, int C, int H, int W, float *out, void *stream);
 RGBD_API int rgbd_depth_head_bwd(const float *h, const float *g_out, int B, int C, int H, int W, float *g_h, void *stream);
 
+/* warp (:171-175) / inv_warp (:178-182): new_zp[b,n,:] = M[b] (z[b,n] * p[:,n]) - cv[b]
+ * with p = (col,row,1) (:59-61).  z: (B,HW); new_zp: (B,HW,3).  inv_warp passes cv = -(K t). */
 RGBD_API int rgbd_warp_fwd(const float *z, const float *M, const float *cv, int B, int H, int W,
                   float *new_zp, void *stream);
 /* g_z (B,HW) = sum_k (M[b]^T g_new_zp[b,n,:])_k p_k[n]   (autograd of F.matmul and z * p) */

@@ -40,6 +40,11 @@ class DvParams(ctypes.Structure):
                 ("voxel_size", c_float), ("near_plane", c_float)]
 
 
+class PosePrior(ctypes.Structure):
+    """rgbd_pose_prior"""
+    _fields_ = [("camera_param_range", ctypes.c_double * 6), ("uniform_distribution", c_int)]
+
+
 class DvRenderParams(ctypes.Structure):
     """rgbd_dv_render_params"""
     _fields_ = [("nf", c_int), ("depth_steps", c_int), ("threshold", c_float), ("inv_c1", c_float), ("inv_c2", c_float)]
@@ -62,6 +67,12 @@ SIGNATURES = {
     "rgbd_consistency_status": (c_int, [c_void, c_void, ctypes.POINTER(c_int)]),
     "rgbd_depth_head_fwd": (c_int, [c_void, c_int, c_int, c_int, c_int, c_void, c_void]),
     "rgbd_depth_head_bwd": (c_int, [c_void, c_void, c_int, c_int, c_int, c_int, c_void, c_void]),
+    "rgbd_pose_sample": (c_int, [ctypes.POINTER(PosePrior), c_int, c_void, ctypes.c_ulonglong, ctypes.c_ulonglong, c_void,
+                                 c_void]),
+    "rgbd_pose_camera_matrices": (c_int, [c_void, c_void, c_int, ctypes.POINTER(c_int), c_void, c_void]),
+    "rgbd_pose_algebra": (c_int, [c_void, c_void, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float)] + [c_void] * 5),
+    "rgbd_pose_pipeline": (c_int, [ctypes.POINTER(PosePrior), c_int, c_void, ctypes.c_ulonglong, ctypes.c_ulonglong,
+                                   ctypes.POINTER(c_int), ctypes.POINTER(c_float), ctypes.POINTER(c_float)] + [c_void] * 7),
     "rgbd_debug_div2": (c_int, [ctypes.c_ulonglong, ctypes.c_uint, c_int, c_int, c_void, c_void]),
     "rgbd_debug_mega_schedule": (c_int, [c_int] * 7 + [ctypes.POINTER(c_int), c_int, ctypes.POINTER(c_int)]),
     "rgbd_consistency_fwd": (c_int, [c_void] * 6 + [c_int] * 4 + [ctypes.POINTER(LossOpts), c_void, c_void, c_void,

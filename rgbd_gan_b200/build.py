@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "librgbdgan_b200.so")
-SOURCES = ["api.cu", "consistency.cu", "deepvoxels.cu"]
+SOURCES = ["api.cu", "consistency.cu", "deepvoxels.cu", "poses.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "sweep.cuh"),
            os.path.join(os.path.dirname(_HERE), "include", "rgbdgan_b200.h")]
 

@@ -131,6 +131,65 @@ class ConsistencyLoss(FunctionNode):
         return _select((g_img, g_rot), target_input_indexes)
 
 
+# ------------------------------------------------------------------------------------ pose pipeline on the device
+def _f9(a):
+    a = np.ascontiguousarray(np.asarray(as_numpy(a), dtype=np.float32)[:3, :3]).reshape(9)
+    return (ctypes.c_float * 9)(*a.tolist())
+
+
+def pose_algebra_device(K, inv_K, theta, theta_rot, xp=None, lib=None):
+    """common/loss_functions.py:85-91 + the constants of :174 / :181 from DEVICE cam2world matrices (B,4,4):
+    rgbd_pose_algebra, no host synchronisation.  Returns device arrays M (B,3,3), c (B,3,1), Mi (B,3,3), ci (B,3,1)."""
+    xp = _xp_of(theta, xp)
+    lib = lib if lib is not None else _lib
+    theta, theta_rot = _f32c(xp, theta), _f32c(xp, theta_rot)
+    B = int(theta.shape[0])
+    M, c = xp.empty((B, 3, 3), dtype="float32"), xp.empty((B, 3, 1), dtype="float32")
+    Mi, ci = xp.empty((B, 3, 3), dtype="float32"), xp.empty((B, 3, 1), dtype="float32")
+    lib.call("rgbd_pose_algebra", _ptr(theta), _ptr(theta_rot), B, _f9(K), _f9(inv_K), _ptr(M), _ptr(c), _ptr(Mi), _ptr(ci),
+             _stream(xp))
+    return M, c, Mi, ci
+
+
+def get_camera_matries(thetas, order=(0, 1, 2), cos_sin=None, xp=None, lib=None):
+    """updater.py:45-60 on the device: (N,6) thetas -> (N,4,4) cam2world.  cos_sin (N,6) = [cos | sin] of the angles as
+    the caller's array library computed them (updater.py:316-317 computes exactly these for the generator) makes the
+    result bit-identical to the reference's NumPy path."""
+    xp = _xp_of(thetas, xp)
+    lib = lib if lib is not None else _lib
+    thetas = _f32c(xp, thetas)
+    cs = None if cos_sin is None else _f32c(xp, cos_sin)
+    n = int(thetas.shape[0])
+    cam = xp.empty((n, 4, 4), dtype="float32")
+    lib.call("rgbd_pose_camera_matrices", _ptr(thetas), _ptr(cs), n, (ctypes.c_int * 3)(*[int(o) for o in order]), _ptr(cam),
+             _stream(xp))
+    return cam
+
+
+class CameraParamPrior:
+    """train_rgbd.py:192-217 on the device: sample(batch_size) -> (batch_size, 6) float32 device array.  draws=None:
+    Philox keyed by (seed, call counter, pair); draws (B,15) float64 replays a host np.random stream bit for bit."""
+
+    def __init__(self, config, xp=None, seed=0, lib=None):
+        rng = [config.x_rotate, config.y_rotate, config.z_rotate, config.x_translate, config.y_translate, config.z_translate]
+        self.camera_param_range = np.array(rng, dtype=np.float64)
+        self.rotation_range = self.camera_param_range[:3]
+        self.uniform = bool(config.uniform_distribution)
+        self.xp = xp if xp is not None else cupy
+        self.seed, self.step = int(seed), 0
+        self._lib = lib if lib is not None else _lib
+        self.c_prior = _lib.PosePrior((ctypes.c_double * 6)(*self.camera_param_range.tolist()), int(self.uniform))
+
+    def sample(self, batch_size, draws=None):
+        xp, B = self.xp, batch_size // 2
+        thetas = xp.empty((2 * B, 6), dtype="float32")
+        d = None if draws is None else xp.ascontiguousarray(xp.asarray(draws), dtype="float64")
+        self._lib.call("rgbd_pose_sample", ctypes.byref(self.c_prior), B, _ptr(d), self.seed, self.step, _ptr(thetas),
+                       _stream(xp))
+        self.step += 1
+        return thetas
+
+
 # ------------------------------------------------------------------------------------ warp / inv_warp / bilinear
 class Warp(FunctionNode):
     """warp / inv_warp (common/loss_functions.py:171-182) with the constant factors M = K R K^-1, cv folded on the
@@ -264,8 +323,12 @@ class LossFuncRotate:
             self.init_params(xp, size=img.shape[-1])
         if hasattr(theta, "array") and not isinstance(theta, np.ndarray):                   # :82-84
             theta, theta_rot = theta.array, theta_rot.array
-        M, c, Mi, ci = pose_algebra(self.K, self.inv_K, theta, theta_rot)
         B, C, H, W = img.shape
+        if not isinstance(theta, np.ndarray) and not isinstance(theta, (list, tuple)) and not debug:
+            # device arrays (the reference's production case, updater.py:315): one small kernel, no .get() sync
+            M, c, Mi, ci = pose_algebra_device(self.K, self.inv_K, theta, theta_rot, xp=xp, lib=self._lib)
+        else:
+            M, c, Mi, ci = pose_algebra(self.K, self.inv_K, theta, theta_rot)
         if debug:                                           # :100-102 -- the six intermediates
             z = _arr(img)[:, -1:].reshape(B, 1, -1)
             z_rot = _arr(img_rot)[:, -1:].reshape(B, 1, -1)

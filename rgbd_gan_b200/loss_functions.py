@@ -60,9 +60,14 @@ class _PoseUploader:
         hv[21 * B:24 * B] = ci.reshape(-1)
         dev = host.to(device, non_blocking=True)
         ev = torch.cuda.Event()
-        ev.record()
+        ev.record(torch.cuda.current_stream(device))
         s["events"][k] = ev
         return dev
+
+
+def unpack_poses(poses, B):
+    return (poses[:9 * B].view(B, 3, 3), poses[9 * B:12 * B].view(B, 3, 1), poses[12 * B:21 * B].view(B, 3, 3),
+            poses[21 * B:24 * B].view(B, 3, 1))
 
 
 def _pose_ptrs(dev, B):
@@ -223,10 +228,13 @@ class LossFuncRotate:
 
     # -- :63-146
     def __call__(self, img, theta, img_rot, theta_rot, occlusion_aware=False, debug=False, max_depth=None,
-                 min_depth=None, depth_hinge=None):
+                 min_depth=None, depth_hinge=None, poses=None):
         """Reference signature (:63-64) plus `depth_hinge=(depth_min, lambda_depth)`: the term the updaters add
         right after this call, loss_rotate += mean(relu(depth_min - x_fake[:, -1]) ** 2) * lambda_depth
-        (updater.py:357-359), evaluated inside the same kernels; the returned loss then includes it."""
+        (updater.py:357-359), evaluated inside the same kernels; the returned loss then includes it.
+        `poses`: the packed pose constants of pose_pipeline.PosePipeline.step / pose_algebra_device (theta and
+        theta_rot are then ignored).  Host (NumPy) thetas take the reference's NumPy matmul sequence on the host;
+        CUDA-tensor thetas take the device pose kernel (bit-identical on the golden vectors, no synchronisation)."""
         img = _dev_f32(img, "img")
         img_rot = _dev_f32(img_rot, "img_rot")
         if img.shape != img_rot.shape or img.dim() != 4:
@@ -236,12 +244,25 @@ class LossFuncRotate:
         if self.size != img.shape[-1]:
             self.init_params(self.xp, size=img.shape[-1])
         B, C, H, W = img.shape
-        M, c, Mi, ci = pose_algebra(self.K, self.inv_K, theta, theta_rot)
-        if debug:
+        if poses is None and isinstance(theta, torch.Tensor) and theta.is_cuda and not debug:
+            # cam2world matrices already on the device (the reference's production case: xp.array(...) thetas,
+            # updater.py:315): R, t and the warp constants come from one small kernel, no D2H sync, no upload
+            from .pose_pipeline import pose_algebra_device
+            poses = pose_algebra_device(self.K, self.inv_K, theta.detach(), theta_rot.detach())
+        if poses is None:
+            M, c, Mi, ci = pose_algebra(self.K, self.inv_K, theta, theta_rot)
+            if debug:
+                return self._debug(img, img_rot, M, c, Mi, ci)
+            with torch.cuda.device(img.device):
+                poses = self._uploader.upload(M, c, Mi, ci, img.device)
+        elif debug:
+            M, c, Mi, ci = (a.cpu().numpy() for a in unpack_poses(poses, B))
             return self._debug(img, img_rot, M, c, Mi, ci)
-        poses = self._uploader.upload(M, c, Mi, ci, img.device)
+        elif poses.numel() != 24 * B or not poses.is_cuda:
+            raise ValueError("poses must be the packed (24*B,) CUDA tensor of pose_pipeline.pose_algebra_device")
         opts = self._opts(occlusion_aware, max_depth, min_depth, B, depth_hinge)
-        return _ConsistencyFn.apply(img, img_rot, self, poses, opts, bool(self.return_new_zp))
+        with torch.cuda.device(img.device):
+            return _ConsistencyFn.apply(img, img_rot, self, poses, opts, bool(self.return_new_zp))
 
     def _debug(self, img, img_rot, M, c, Mi, ci):
         """:100-102 -- warped images / masks for eyeballing"""
@@ -249,8 +270,9 @@ class LossFuncRotate:
         dev = img.device
         z = img[:, -1:].reshape(B, 1, -1)
         z_rot = img_rot[:, -1:].reshape(B, 1, -1)
-        new_zp = _WarpFn.apply(z, torch.from_numpy(M).to(dev), torch.from_numpy(c).to(dev), H, W)
-        new_zp_rot = _WarpFn.apply(z_rot, torch.from_numpy(Mi).to(dev), torch.from_numpy(ci).to(dev), H, W)
+        with torch.cuda.device(dev):
+            new_zp = _WarpFn.apply(z, torch.from_numpy(M).to(dev), torch.from_numpy(c).to(dev), H, W)
+            new_zp_rot = _WarpFn.apply(z_rot, torch.from_numpy(Mi).to(dev), torch.from_numpy(ci).to(dev), H, W)
         warped, not_out = bilinear(img_rot, new_zp)
         warped_rot, not_out_rot = bilinear(img, new_zp_rot)
         return warped, not_out, new_zp, warped_rot, not_out_rot, new_zp_rot
@@ -310,14 +332,16 @@ def warp(K, inv_K, R, t, z, p):
     """common/loss_functions.py:171-175: (K R K^-1)(z p) - (K R) t, returned as (B,HW,3). Differentiable in z."""
     H, W = _grid_dims(p, z.shape[-1])
     M, cv = warp_constants(K, inv_K, R, t, inverse=False)
-    return _WarpFn.apply(z, torch.from_numpy(M).to(z.device), torch.from_numpy(cv).to(z.device), H, W)
+    with torch.cuda.device(z.device):
+        return _WarpFn.apply(z, torch.from_numpy(M).to(z.device), torch.from_numpy(cv).to(z.device), H, W)
 
 
 def inv_warp(K, inv_K, inv_R, t, z, p):
     """common/loss_functions.py:178-182: (K R^T K^-1)(z p) + K t, returned as (B,HW,3). Differentiable in z."""
     H, W = _grid_dims(p, z.shape[-1])
     M, cv = warp_constants(K, inv_K, inv_R, t, inverse=True)
-    return _WarpFn.apply(z, torch.from_numpy(M).to(z.device), torch.from_numpy(cv).to(z.device), H, W)
+    with torch.cuda.device(z.device):
+        return _WarpFn.apply(z, torch.from_numpy(M).to(z.device), torch.from_numpy(cv).to(z.device), H, W)
 
 
 class _BilinearFn(torch.autograd.Function):
@@ -351,7 +375,8 @@ def bilinear(img, zp):
     b, hw, _ = zp.shape
     if img.shape[0] != b or img.shape[2] * img.shape[3] != hw:
         raise ValueError("zp must be (B, H*W, 3) matching img (B,C,H,W)")
-    return _BilinearFn.apply(img, zp)
+    with torch.cuda.device(img.device):
+        return _BilinearFn.apply(img, zp)
 
 
 class _DepthHeadFn(torch.autograd.Function):
@@ -376,7 +401,9 @@ class _DepthHeadFn(torch.autograd.Function):
 def depth_head(h):
     """"next" row: the generators' depth head (net.py:294-299, :756-761) as one kernel --
     F.concat([h[:, :-1], 1 / (F.softplus(h[:, -1:]) + 1e-4)]); differentiable in h"""
-    return _DepthHeadFn.apply(_dev_f32(h, "h"))
+    h = _dev_f32(h, "h")
+    with torch.cuda.device(h.device):
+        return _DepthHeadFn.apply(h)
 
 
-__all__ = ["LossFuncRotate", "warp", "inv_warp", "bilinear", "pose_algebra", "combine_loss_parts", "depth_head"]
+__all__ = ["LossFuncRotate", "warp", "inv_warp", "bilinear", "pose_algebra", "combine_loss_parts", "depth_head", "unpack_poses"]
