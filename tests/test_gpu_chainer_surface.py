@@ -21,7 +21,7 @@ torch = pytest.importorskip("torch")
 sys.path.insert(0, GOLDEN)
 import chainer_shim  # noqa: E402
 
-_DT = {"float32": "float32", "uint8": "uint8", "int32": "int32", "bool": "bool"}
+_DT = {"float32": "float32", "float64": "float64", "uint8": "uint8", "int32": "int32", "bool": "bool"}
 
 
 def _tdt(dtype):
@@ -232,3 +232,33 @@ def test_render_node_on_cupy_style_arrays(nodes):
     torch.cuda.synchronize()
     for gv, key in zip(grads, ("g_grid", "g_W1", "g_b1", "g_W2", "g_b2")):
         assert rel(gv.array.get().reshape(g[key].shape), g[key]) <= 1e-5, key
+
+
+def test_pose_pipeline_on_cupy_style_arrays(nodes):
+    """SURVEY 8f rank 4 on the Chainer / CuPy surface: device cam2world matrices (what the reference's updater holds after
+    xp.array(get_camera_matries(thetas)), updater.py:315) go through rgbd_pose_algebra -- no .get() -- and give the
+    golden new_zp bit for bit; get_camera_matries / CameraParamPrior work on cupy-style arrays"""
+    from oracle import numpy_port as npp
+    g = load_golden("loss_cfg0_l1_occ")
+    o = case_options(g)
+    B = o["B"]
+    xp = TorchXP()
+    f = nodes.LossFuncRotate(xp, lambda_geometric=o["lam"], grad_scale=1.0)
+    img, img_rot = _V(xp, g["x"][:B]), _V(xp, g["x"][B:])
+    cam = xp.asarray(g["cam"])
+    loss, zp = f(img, cam[:B], img_rot, cam[B:], occlusion_aware=o["occ"])
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(zp.array.get(), g["new_zp_cat"])
+    assert abs(float(loss.array.get()) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    th = g["thetas"]
+    cs = np.concatenate([np.cos(th[:, :3]), np.sin(th[:, :3])], axis=1).astype(np.float32)
+    got = nodes.get_camera_matries(xp.asarray(th), cos_sin=xp.asarray(cs), xp=xp).get()
+    np.testing.assert_allclose(got, g["cam"], rtol=0, atol=5e-7)
+    cfg = types.SimpleNamespace(x_rotate=0.3054, y_rotate=1.0472, z_rotate=0, x_translate=0, y_translate=0, z_translate=0,
+                                uniform_distribution=False)
+    np.random.seed(4)
+    u, e, s = np.random.uniform(-1, 1, (B, 6)), np.random.uniform(0, 0.5, (B, 6)), np.random.choice(2, (B, 3))
+    np.random.seed(4)
+    want = npp.sample_camera_prior(2 * B, npp.FFHQ_RANGES, False)
+    got = nodes.CameraParamPrior(cfg, xp=xp).sample(2 * B, draws=np.concatenate([u, e, s.astype(np.float64)], 1)).get()
+    np.testing.assert_array_equal(got, want)
