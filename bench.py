@@ -175,6 +175,7 @@ class Harness:
         self.lib = _lib.load()
         self.hbm_peak, self.peak_src = peaks()
         self.peer = None
+        self.exchange = getattr(a, "exchange", "lazy")
         if self.world > 1 and a.collective == "peer":
             from rgbd_gan_b200.distributed import PeerComm
             self.peer = PeerComm()            # fused 20-byte all-reduce inside the finalize kernel (NVLink peer memory)
@@ -225,11 +226,15 @@ class Workload:
         self.ws = torch.empty(h.lib.rgbd_consistency_workspace_bytes(B, C, S, S), dtype=torch.uint8, device=h.dev)
         nan = float("nan")
         ng = n_global if n_global is not None else B * h.world
-        # N > 1: the loss exchange is deferred (it overlaps the next call; joined at the end of the timed region,
-        # inside it); `joined` makes every call wait for its own exchange instead.  Gradients are never deferred
+        # N > 1, --exchange: "lazy" (default) = every call PUBLISHES its loss parts into the peers' mailboxes from its own
+        # finishing kernel and nobody waits; the sum is formed when the loss is read (rgbd_peer_comm_wait: at the end of
+        # the timed region, inside it) -- a training loop only logs the loss (updater.py:361).  "deferred" = all-reduce
+        # every call on a side stream, lag bounded to one call; "joined" = every call waits for its own all-reduce.
+        # Gradients are never deferred
+        defer = {"lazy": 2, "deferred": 1, "joined": 0}[h.exchange] if h.peer is not None else 0
         self.opts = _lib.LossOpts(_lib.NORM_L1, 1, nan if max_depth is None else max_depth,
                                   nan if min_depth is None else min_depth, lam, ng,
-                                  h.peer.handle if h.peer is not None else None, 1 if h.peer is not None else 0, 0)
+                                  h.peer.handle if h.peer is not None else None, defer, 0)
         self.opts_local = _lib.LossOpts(_lib.NORM_L1, 1, nan if max_depth is None else max_depth,
                                         nan if min_depth is None else min_depth, lam, ng, None, 0, 0)
         if hinge is not None:
@@ -535,9 +540,14 @@ def run_ours(a):
 
     line = None
     if h.rank == 0:
-        coll = "none" if h.world == 1 else (
-            "own finalize kernel exchanges them over NVLink peer memory on a side stream; deferred by one call, the last "
-            "one joined inside the timed region" if h.peer is not None else "NCCL on a side stream")
+        coll = "none" if h.world == 1 else ({
+            "lazy": "the kernel that finishes the loss publishes its 5 values into every peer's mailbox over NVLink peer memory "
+                    "each call (no wait, at most 7 calls ahead of the slowest rank); summed in rank order when the loss is read: "
+                    "once, at the end of the timed region, inside it",
+            "deferred": "own finalize kernel all-reduces them over NVLink peer memory on a side stream; deferred by one call, the "
+                        "last one joined inside the timed region",
+            "joined": "own finalize kernel all-reduces them over NVLink peer memory; every call joined"}[h.exchange]
+            if h.peer is not None else "NCCL on a side stream")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": h.world, "steps": a.steps, "warmup": a.warmup,
             "prewarm_steps": PREWARM_STEPS + 3, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -801,6 +811,8 @@ def main():
     ap.add_argument("--graph", action="store_true", help="(ignored: direct PDL-chained launches are the measured default)")
     ap.add_argument("--no-graph", action="store_true", help="(default; kept for compatibility)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--exchange", default="lazy", choices=["lazy", "deferred", "joined"],
+                    help="N > 1 with --collective peer: when the exchanged loss parts are summed (see Workload)")
     ap.add_argument("--no-sweep", action="store_true", help="skip the single-GPU sub-records (DeepVoxels, hinge, ...)")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configurations")
     ap.add_argument("--no-cpu", action="store_true")

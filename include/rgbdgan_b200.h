@@ -78,7 +78,14 @@ typedef struct {
                              gradients are ordered on `stream` as usual, loss_parts become valid
                              after rgbd_peer_comm_wait(comm, stream) (or the next loss call on this
                              comm).  The exchange then overlaps the stage-out of this call and the
-                             stage-in of the next one.  Not usable under CUDA-graph stream capture. */
+                             stage-in of the next one.  Not usable under CUDA-graph stream capture.
+                             2 = publish only: the kernel that finishes the loss pushes this rank's parts into
+                             every peer's mailbox (posted NVLink stores, no wait, no side stream, no events:
+                             capturable) and leaves THIS SHARD's values in loss_parts; rgbd_peer_comm_wait(comm,
+                             stream) then sums the latest call's parts of all ranks in rank order into that
+                             call's loss_parts (which must still be alive).  The GPUs of a box are not coupled
+                             step by step: a rank may run up to 7 calls ahead of the slowest one.  Every rank
+                             must call rgbd_peer_comm_wait at the same point of its call sequence.          */
     int reserved;
     float hinge_depth_min; /* "next" row fused around the loss (updater.py:357-359, C == 4 only):        */
     float hinge_lambda;    /* loss_rotate += mean(relu(depth_min - depth)^2) * lambda_depth over both      */
@@ -169,7 +176,7 @@ RGBD_API int rgbd_consistency_rescale(float *g_img, float *g_img_rot, size_t n_e
  * ranks that shard the pairs (the reference's analogue is ChainerMN's pure_nccl communicator,
  * train_rgbd.py:103-113).  Instead of a separate NCCL launch, the finalize kernel of
  * rgbd_consistency_fwd / _fwd_bwd exchanges the 16 bytes itself over NVLink peer memory:
- *   1. every rank: rgbd_peer_comm_create(rank, world, &comm, handle)   (allocates a 4 KB mailbox)
+ *   1. every rank: rgbd_peer_comm_create(rank, world, &comm, handle)   (allocates a 10 KB mailbox)
  *   2. all-gather the 64-byte handles with any host-side transport (torch.distributed, MPI)
  *   3. every rank: rgbd_peer_comm_connect(comm, all_handles (world*64 bytes, rank order))
  *   4. set rgbd_loss_opts.peer_comm = comm and n_pairs_global = total pairs; every rank must make
@@ -179,12 +186,14 @@ RGBD_API int rgbd_consistency_rescale(float *g_img, float *g_img_rot, size_t n_e
 RGBD_API int rgbd_peer_comm_create(int rank, int world, void **comm_out, unsigned char *ipc_handle_out);
 RGBD_API int rgbd_peer_comm_connect(void *comm, const unsigned char *all_handles);
 RGBD_API int rgbd_peer_comm_destroy(void *comm);
-/* make `stream` wait for the most recent (deferred) loss exchange of this comm */
+/* make `stream` wait for the most recent (deferred) loss exchange of this comm; after defer_loss == 2 calls: launch the
+ * kernel that sums the latest call's published parts into its loss_parts */
 RGBD_API int rgbd_peer_comm_wait(void *comm, void *stream);
 /* Health of the exchange: every wait for a peer's flag inside the finalize kernel is bounded (2 s, env
  * RGBD_B200_PEER_TIMEOUT_MS); a wait that expires -- a rank died, or made a different sequence of loss calls --
  * raises a sticky flag instead of hanging every GPU of the box, and the loss parts of that call are undefined.
- * Synchronises the comm's side stream and `stream`; *status_host = 0 ok, 1 a wait timed out. */
+ * Synchronises the comm's side stream and `stream`; *status_host = 0 ok, 1 a wait timed out (or, defer_loss == 2, a
+ * peer overwrote an epoch before it was summed: the ranks made different call sequences). */
 RGBD_API int rgbd_peer_comm_status(void *comm, void *stream, int *status_host);
 /* Test aid: instead of rgbd_peer_comm_connect, point every OTHER rank's mailbox at a local buffer nobody writes
  * (single process, single GPU): the next sharded loss call then exercises the bounded wait. */

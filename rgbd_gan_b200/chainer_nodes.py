@@ -295,7 +295,7 @@ class LossFuncRotate:
         self.p = None
         self.grad_scale = grad_scale
         self.peer_comm, self.n_pairs_global = peer_comm, n_pairs_global
-        self.defer_loss = bool(defer_loss) and peer_comm is not None
+        self.defer_loss = (2 if defer_loss == "lazy" else int(bool(defer_loss))) if peer_comm is not None else 0
         self._lib = lib if lib is not None else _lib
         self._ws = None
 

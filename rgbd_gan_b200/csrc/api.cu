@@ -122,6 +122,7 @@ RGBD_API int rgbd_peer_comm_wait(void *comm, void *stream)
     using namespace rgbd;
     rgbd_peer_comm *pc = (rgbd_peer_comm *)comm;
     if (!pc) { set_error("rgbd_peer_comm_wait: null comm"); return RGBD_E_ARG; }
+    if (pc->lazy_pending) return launch_peer_collect(pc, (cudaStream_t)stream);
     if (!pc->fin_pending) return 0;
     const cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, pc->ev_fin_done, 0);
     if (e != cudaSuccess) { set_error("rgbd_peer_comm_wait: %s", cudaGetErrorString(e)); return (int)e; }

@@ -20,19 +20,27 @@ void set_error(const char *fmt, ...);
 int check_launch(const char *what);
 void count_launch(int n = 1);                       // bookkeeping for rgbd_launch_count()
 extern thread_local cudaEvent_t g_hook_start, g_hook_stop;   // rgbd_profile_hook()
+struct rgbd_peer_comm;
+int launch_peer_collect(rgbd_peer_comm *pc, cudaStream_t st);   // consistency.cu: finishes a publish-only exchange
 
 // ---- peer-memory mailbox for the fused loss all-reduce (one per rank, cudaMalloc + CUDA IPC)
 constexpr int kMaxPeers = 16;
+constexpr int kLazyDepth = 8;         // publish-only mode: ring of epochs a rank may run ahead of the slowest peer
 struct rgbd_mailbox {
     float slot[2][kMaxPeers][8];      // [epoch parity][writer rank][4 loss means, depth hinge, 3 spare]
     unsigned flag[2][kMaxPeers];      // epoch published by each writer
     unsigned epoch;                   // local: last completed epoch
-    unsigned error;                   // local, sticky: a wait for a peer's flag ran into the time limit
-    unsigned pad[30];
+    unsigned error;                   // local, sticky: 1 = a wait for a peer's flag ran into the time limit, 2 = a peer
+                                      // overwrote an epoch before it was collected (publish-only mode)
+    unsigned lepoch;                  // local: last epoch this rank published in publish-only mode
+    unsigned pad[29];
+    float lslot[kLazyDepth][kMaxPeers][8];   // publish-only mode: [epoch % kLazyDepth][writer rank][values]
+    unsigned lflag[kLazyDepth][kMaxPeers];   // epoch held by that slot
 };
 struct PeerArgs {
     rgbd_mailbox *box[kMaxPeers];     // box[r] = rank r's mailbox, mapped into this process
     int rank, world;
+    int lazy;                         // 1: publish-only (rgbd_loss_opts.defer_loss == 2), summed by rgbd_peer_comm_wait
     unsigned long long timeout_ns;    // bound of every wait for a peer (a dead / desynchronised rank must not hang the GPU)
 };
 struct rgbd_peer_comm {               // host object behind the opaque handle of the C-ABI
@@ -44,6 +52,10 @@ struct rgbd_peer_comm {               // host object behind the opaque handle of
     cudaEvent_t ev_main_done, ev_fin_done;
     bool fin_pending;                 // ev_fin_done has been recorded and not yet waited on by the main stream
     unsigned long long calls;         // parity selects one of two partial-sum buffers
+    // publish-only mode: what rgbd_peer_comm_wait has to finish (the latest call's output pointer and constants)
+    bool lazy_pending;
+    float *lazy_loss_parts;
+    float lazy_lambda;
     rgbd_mailbox *loopback[kMaxPeers]; // test aid (rgbd_debug_peer_comm_loopback): local stand-ins for absent peers
 };
 

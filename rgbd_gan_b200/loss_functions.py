@@ -159,7 +159,10 @@ class LossFuncRotate:
       defer_loss      -- with peer_comm: the loss exchange is not joined into the current stream; the
                          returned loss is valid after `peer_comm.wait()` (gradients are unaffected).  The
                          exchange then overlaps the rest of the step, as a training loop that only logs
-                         the loss (updater.py:361, chainer.report) allows.
+                         the loss (updater.py:361, chainer.report) allows.  defer_loss="lazy": every call only
+                         publishes its parts to the peers from the kernel that finishes the loss (no wait, no
+                         side stream); `peer_comm.wait()` sums the LATEST call's parts of all ranks -- the GPUs
+                         are not coupled step by step (at most 7 calls apart).
       peer_comm       -- rgbd_gan_b200.distributed.PeerComm: same sharding, but the 4 floats are
                          exchanged inside the loss kernel over NVLink peer memory (no NCCL launch).
     """
@@ -179,7 +182,8 @@ class LossFuncRotate:
         self.process_group = process_group
         self.peer_comm = peer_comm
         self.n_pairs_global = n_pairs_global
-        self.defer_loss = bool(defer_loss) and peer_comm is not None
+        # False / True (all-reduce on a side stream, joined by peer_comm.wait()) / "lazy" (publish only, summed by wait())
+        self.defer_loss = (2 if defer_loss == "lazy" else int(bool(defer_loss))) if peer_comm is not None else 0
         if peer_comm is not None and process_group is not None:
             raise ValueError("give either process_group (NCCL all-reduce) or peer_comm (fused), not both")
         self.last_loss_parts = None

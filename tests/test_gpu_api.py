@@ -224,6 +224,47 @@ def test_peer_exchange_wait_is_bounded(monkeypatch):
     lib.rgbd_peer_comm_destroy(h)
 
 
+def test_publish_only_exchange_on_one_gpu(monkeypatch):
+    """defer_loss == 2 (publish only) with a world-2 comm on ONE GPU whose peer mailbox is a local buffer nobody writes:
+    the loss call itself never waits and leaves the shard's own parts; rgbd_peer_comm_wait (the collect) gives up after
+    the time limit and raises the sticky flag; so does the flow control once the rank is 7 calls ahead of its silent peer"""
+    import ctypes
+    import time
+    from gpu_util import Consistency
+    from oracle import numpy_port as npp
+    from rgbd_gan_b200 import _lib
+    monkeypatch.setenv("RGBD_B200_PEER_TIMEOUT_MS", "20")
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    ipc = ctypes.create_string_buffer(64)
+    _lib.check(lib.rgbd_peer_comm_create(0, 2, ctypes.byref(h), ipc), "create")
+    _lib.check(lib.rgbd_debug_peer_comm_loopback(h), "loopback")
+    g = load_golden("loss_s64_l1_noocc")
+    o = case_options(g)
+    port = npp.LossFuncRotateNP(lambda_geometric=o["lam"])
+    port.init_params(o["S"])
+    drv = Consistency(g["x"], g["cam"], o["B"], port.K, port.inv_K, lam=o["lam"], occ=o["occ"])
+    local, _, _ = drv.fwd_bwd(gy=o["gy"])                          # reference: the same shard without a comm
+    drv.opts.peer_comm, drv.opts.defer_loss = h.value, 2
+    status = ctypes.c_int(-1)
+    t0 = time.perf_counter()
+    for _ in range(6):                                             # fewer than the ring depth: nothing waits
+        parts, gi, gr = drv.fwd_bwd(gy=o["gy"])
+    _lib.check(lib.rgbd_peer_comm_status(h, None, ctypes.byref(status)), "status")
+    assert status.value == 0 and time.perf_counter() - t0 < 2.0
+    np.testing.assert_array_equal(parts[:7], local[:7])            # the shard's own values until the collect
+    assert_grad_close(gi, g["g_img"])                              # gradients never depend on the exchange
+    _lib.check(lib.rgbd_peer_comm_wait(h, None), "wait")           # collect: the peer never published
+    _lib.check(lib.rgbd_peer_comm_status(h, None, ctypes.byref(status)), "status")
+    assert status.value == 1
+    for _ in range(4):                                             # now more than 7 ahead of the silent peer: bounded
+        drv.fwd_bwd(gy=o["gy"])
+    assert time.perf_counter() - t0 < 5.0
+    drv.opts.peer_comm = None
+    torch.cuda.synchronize()
+    lib.rgbd_peer_comm_destroy(h)
+
+
 def test_occupancy_net_loss_and_calc_real_pos_smoke():
     """LossFuncRotate.calc_real_pos (:148-158) against the NumPy expression and occupancy_net_loss (:160-168) end to
     end with a stand-in occupancy network: finite scalar, gradient reaches the network and the depth"""

@@ -38,20 +38,24 @@ def _worker(rank, world, port, name, out_dir):
     x = torch.from_numpy(g["x"]).cuda()
     res = {}
     comm = PeerComm()
-    for mode in ("peer", "nccl", "peer_fused", "peer_deferred"):
+    for mode in ("peer", "nccl", "peer_fused", "peer_deferred", "peer_lazy"):
         kw = dict(peer_comm=comm) if mode.startswith("peer") else dict(process_group=dist.group.WORLD)
-        if mode in ("peer_fused", "peer_deferred"):
+        if mode in ("peer_fused", "peer_deferred", "peer_lazy"):
             kw["grad_scale"] = o["gy"]
         if mode == "peer_deferred":
             kw["defer_loss"] = True
+        if mode == "peer_lazy":
+            kw["defer_loss"] = "lazy"             # publish only; summed by comm.wait()
         f = LossFuncRotate(None, norm=o["norm"], lambda_geometric=o["lam"], n_pairs_global=B, **kw)
-        for rep in range(3):                      # several calls: epochs advance, mailbox slots are reused
+        for rep in range(20 if mode == "peer_lazy" else 3):   # several calls: epochs advance, mailbox slots are reused
             img = x[:B][lo:hi].clone().requires_grad_(True)
             img_rot = x[B:][lo:hi].clone().requires_grad_(True)
             loss, _ = f(img, g["cam"][:B][lo:hi], img_rot, g["cam"][B:][lo:hi], occlusion_aware=o["occ"])
             (loss * o["gy"]).backward()
-        if mode == "peer_deferred":
+        if mode in ("peer_deferred", "peer_lazy"):
             comm.wait()                           # only now may the loss be read
+        if mode == "peer_lazy":
+            res["lazy_status"] = np.int32(comm.status())
         res[mode + "_loss"] = loss.detach().cpu().numpy()
         res[mode + "_gi"] = img.grad.cpu().numpy()
         res[mode + "_gr"] = img_rot.grad.cpu().numpy()
@@ -69,7 +73,8 @@ def test_sharded_pairs_two_gpus(name, tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), name, str(tmp_path)), nprocs=world, join=True)
     g = load_golden(name)
     outs = [np.load(tmp_path / ("rank%d.npz" % r)) for r in range(world)]
-    for mode in ("peer", "nccl", "peer_fused", "peer_deferred"):
+    assert all(int(d["lazy_status"]) == 0 for d in outs)
+    for mode in ("peer", "nccl", "peer_fused", "peer_deferred", "peer_lazy"):
         for d in outs:
             assert abs(float(d[mode + "_loss"]) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
             lo, hi = int(d["lo"]), int(d["hi"])
