@@ -446,6 +446,37 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
             if (LOSS && a.hinge_partials) a.hinge_partials[(size_t)dir * ncta + cta] = h;
             if (GRAD && RING && dir == 0) a.ovf_count[cta] = *scount;
         }
+        if (GRAD && RING) {
+            // tail: the last kSwReach blocks can only be written back now.  The 4 retire warps would do them one after the
+            // other (an L2 round trip each, ~5 us with 16 idle warps); here every compute warp takes one (image, row) item
+            // per block.  All compute warps have passed the barrier above, i.e. every RED into the ring has been issued
+            // (CTA-scope fence at the end of each step); the ring needs no re-zeroing (the next launch zeroes it).
+            fence_cta();
+            float scale = a.scale;
+            if (a.scale_dev) scale *= __ldg(a.scale_dev);
+            const float4 *ringc = a.ring + (size_t)cta * 2 * kSwRingRows * W;
+            const int X0 = LBe - kSwReach > LBs ? LBe - kSwReach : LBs;
+            const int sel = warp / kSwR, r = warp % kSwR;                  // 16 warps = 2 images x 8 rows
+            float4 v[kSwReach][W / 32];
+#pragma unroll
+            for (int n = 0; n < kSwReach; ++n)
+                if (X0 + n < LBe) {
+                    const float4 *src = ringc + ((size_t)sel * kSwRingRows + (((X0 + n) * kSwR + r) & (kSwRingRows - 1))) * W + lane;
+#pragma unroll
+                    for (int k = 0; k < W / 32; ++k) v[n][k] = ld_cg_v4(src + 32 * k);
+                }
+#pragma unroll
+            for (int n = 0; n < kSwReach; ++n)
+                if (X0 + n < LBe) {
+                    const int X = X0 + n, pp = X / a.bpp, jj = X - pp * a.bpp;
+                    float *dst = (sel ? a.g_img_rot : a.g_img) + (size_t)pp * 4 * HW + (size_t)(jj * kSwR + r) * W + lane;
+#pragma unroll
+                    for (int k = 0; k < W / 32; ++k) {
+                        __stcs(dst + 32 * k, v[n][k].x * scale); __stcs(dst + HW + 32 * k, v[n][k].y * scale);
+                        __stcs(dst + 2 * (size_t)HW + 32 * k, v[n][k].z * scale); __stcs(dst + 3 * (size_t)HW + 32 * k, v[n][k].w * scale);
+                    }
+                }
+        }
     } else {
         // ------------------------------------------------------------------ retire warps (warp 0, lane 0 also drives the TMA)
         const int rw = warp - kSwComputeWarps;
@@ -534,8 +565,7 @@ __global__ void __launch_bounds__(kSwThreads, 1) k_consistency_sweep(const Sweep
                 if (lane == 0) mbar_arrive(bar_zero + 8 + 8 * (t & 3));
             }
         }
-        if (retire)
-            for (int X = (LBe - kSwReach > LBs ? LBe - kSwReach : LBs); X < LBe; ++X) retire_block(X);
+        // (the last kSwReach blocks are written back by the compute warps, see the end of their branch)
     }
 }
 
