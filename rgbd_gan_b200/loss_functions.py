@@ -201,6 +201,10 @@ class LossFuncRotate:
         ws = self._ws.get(key)
         if ws is None:
             nbytes = _lib.load().rgbd_consistency_workspace_bytes(B, C, H, W)
+            if self._ws and self.peer_comm is not None and self.defer_loss == 1:
+                # a deferred exchange of the previous call may still read the old workspace's partial sums on the
+                # comm's side stream: order it before the old buffer can be reused by the allocator
+                self.peer_comm.wait()
             ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
             self._ws = {key: ws}                       # keep one size only
         return ws
