@@ -290,9 +290,9 @@ class Workload:
 
     def timed(self, steps, warmup, step=None, sampler=None):
         """EXACTLY `steps` steps, CUDA events on the launch stream, max over ranks.  Sequence: `warmup` untimed steps,
-        barrier + device sync, ONE untimed step whose loss exchange is joined (at N > 1 every GPU leaves it within
-        microseconds of the others, so the ranks enter the timed region aligned and the NCCL barrier's exit skew stays
-        outside), e0, `steps` steps, join of the last exchange, e1, barrier + device sync."""
+        barrier + device sync, ALIGN_STEPS untimed steps the last of which has its loss exchange joined (at N > 1 every
+        GPU leaves it within microseconds of the others, so the ranks enter the timed region aligned and the NCCL
+        barrier's exit skew stays outside), e0, `steps` steps, join of the last exchange, e1, barrier + device sync."""
         h, torch = self.h, self.h.torch
         step = step or self.step_fused
         pool, n = self.pool, self.pool_n
@@ -310,7 +310,11 @@ class Workload:
                 h.stream.wait_stream(h.comm)
             self.join_exchange()
             h.barrier()
-            one(warmup)                                          # alignment step (untimed)
+            # alignment steps (untimed, stream-ordered right in front of e0 with no host gap): the barrier, the device
+            # sync and the start of the clock sampler leave the GPU idle for milliseconds; a 20-step timed region right
+            # after that measured 4 % slower than the steady state (126.7 vs 121.9 us).  The last one is joined
+            for k in range(ALIGN_STEPS):
+                one(warmup + k)
             if h.comm is not None:
                 h.stream.wait_stream(h.comm)
             self.join_exchange()
@@ -319,7 +323,7 @@ class Workload:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(h.stream)
             for k in range(steps):
-                one(warmup + 1 + k)
+                one(warmup + ALIGN_STEPS + k)
             if h.comm is not None:
                 h.stream.wait_stream(h.comm)                     # the last all-reduces are inside the timed region
             self.join_exchange()                                 # ... and so is the join of the last deferred exchange
@@ -489,6 +493,7 @@ def workload_config(a, pairs):
             "depth": a.depth, "pose_ranges": "x 0.3054 / y 1.0472 rad (yml)", "upstream_grad": LAMBDA_ROTATE}
 
 
+ALIGN_STEPS = 48                # untimed steps between the barrier and e0 of every timed region (see Workload.timed)
 PREWARM_STEPS = 1500            # fixed count (every rank makes the same sequence of loss calls): ~0.2 s at 256 pairs
 
 
@@ -550,7 +555,7 @@ def run_ours(a):
             if h.peer is not None else "NCCL on a side stream")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": h.world, "steps": a.steps, "warmup": a.warmup,
-            "prewarm_steps": PREWARM_STEPS + 3, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "prewarm_steps": PREWARM_STEPS + 3, "align_steps": ALIGN_STEPS, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             # `config` names the workload only (identical in both arms); how THIS arm ran it is under `run`
             "config": workload_config(a, B),
