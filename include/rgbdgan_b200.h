@@ -278,6 +278,13 @@ RGBD_API size_t rgbd_dv_workspace_bytes(const rgbd_dv_params *p);
 RGBD_API int rgbd_dv_compute_proj_idcs(const rgbd_dv_params *p, const float *cam2world, int32_t *lin_ind,
                               float *voxel_coords, int *M_host, void *workspace,
                               size_t workspace_bytes, void *stream);
+/* the same with the reference's optional grid2world argument (projection.py:48,53-54,83-84; no caller in the reference):
+ * world2grid = inv(grid2world), DEVICE, 16 floats; grid_coords = world2grid . (cam2world . coords), both products in the
+ * sgemm order, so lin_ind / voxel_coords are bit-identical to the reference's (folding the two matrices on the host is
+ * not: 2e-6 on the coordinates) */
+RGBD_API int rgbd_dv_compute_proj_idcs_g2w(const rgbd_dv_params *p, const float *cam2world, const float *world2grid,
+                                           int32_t *lin_ind, float *voxel_coords, int *M_host, void *workspace,
+                                           size_t workspace_bytes, void *stream);
 
 /* interpolate_trilinear (deepvoxel.py:388-428) for ONE sample from explicit index lists:
  * grid (F,G,G,G) -> frustum (F,D,H,W), zero where not listed.  ld = row stride of voxel_coords. */

@@ -329,8 +329,10 @@ class ProjectionHelperNP:
         self.near_plane = f32(near_plane)
         self.frustrum_depth = frustrum_depth
 
-    def compute_proj_idcs(self, cam2world):
+    def compute_proj_idcs(self, cam2world, grid2world=None):
         dims, K = self.projection_image_dims, self.projection_intrinsic
+        if grid2world is not None:
+            world2grid = np.linalg.inv(grid2world)
         n = dims[0] * dims[1] * int(self.frustrum_depth)
         lin = np.arange(0, n).astype("int32")
         coords = np.zeros((4, n), dtype="float32")
@@ -345,6 +347,8 @@ class ProjectionHelperNP:
         coords[1] = (coords[1] - f32(K[1][2])) / f32(K[1][1])
         coords[:2] *= coords[2]
         grid_coords = np.dot(cam2world, coords)
+        if grid2world is not None:
+            grid_coords = np.dot(world2grid, grid_coords)
         vc = grid_coords[:3, :] / f32(self.voxel_size)
         vc = vc + f32(self.grid_dims[2] / 2)
         mask = np.all(vc >= 0, axis=0)

@@ -461,6 +461,57 @@ ORC_API int orc_dv_compute_proj_idcs(const orc_dv_params *P, const float *cam2wo
     return M;
 }
 
+/* the same with the optional grid2world argument (projection.py:53-54,83-84): grid_coords = world2grid . (cam2world .
+ * coords), two sgemm products with K = 4 (all four rows of the first feed the second) */
+static inline int orc_dv_coords_g2w(const orc_dv_params *P, const float *T, const float *Wg, int l, float *vc)
+{
+    const int WH = P->W * P->H;
+    const int d = l / WH;
+    const int tmp = l - d * WH;
+    const float yrow = (float)((double)tmp / (double)P->W);
+    const float xcol = (float)(tmp % P->W);
+    float zc = (float)d * P->voxel_size;
+    zc = zc + P->near_plane;
+    float xc = (xcol - P->cx) / P->fx;
+    float yc = (yrow - P->cy) / P->fy;
+    xc = xc * zc; yc = yc * zc;
+    float gc[4];
+    for (int r = 0; r < 4; ++r) {
+        float g = T[4 * r + 0] * xc;
+        g = fmaf(T[4 * r + 1], yc, g);
+        g = fmaf(T[4 * r + 2], zc, g);
+        gc[r] = fmaf(T[4 * r + 3], 1.0f, g);
+    }
+    int keep = 1;
+    for (int r = 0; r < 3; ++r) {
+        float g = Wg[4 * r + 0] * gc[0];
+        g = fmaf(Wg[4 * r + 1], gc[1], g);
+        g = fmaf(Wg[4 * r + 2], gc[2], g);
+        g = fmaf(Wg[4 * r + 3], gc[3], g);
+        float v = g / P->voxel_size;
+        v = v + (float)P->G / 2.0f;
+        vc[r] = v;
+        keep = keep && (v >= 0.0f) && (v < (float)P->G);
+    }
+    return keep;
+}
+
+ORC_API int orc_dv_compute_proj_idcs_g2w(const orc_dv_params *P, const float *cam2world, const float *world2grid,
+                                         int32_t *lin_ind, float *voxel_coords, int ld)
+{
+    const int n = P->W * P->H * P->D;
+    int M = 0;
+    for (int l = 0; l < n; ++l) {
+        float vc[3];
+        if (orc_dv_coords_g2w(P, cam2world, world2grid, l, vc)) {
+            lin_ind[M] = l;
+            voxel_coords[M] = vc[0]; voxel_coords[ld + M] = vc[1]; voxel_coords[2 * ld + M] = vc[2];
+            ++M;
+        }
+    }
+    return M;
+}
+
 typedef struct { int x0, x1, y0, y1, z0, z1; float wx0, wx1, wy0, wy1, wz0, wz1; } orc_taps;
 
 /* deepvoxel/deepvoxel.py:394-412: axis swap (Q8), truncation, clamp, fp64 fractions (Q7) */

@@ -89,6 +89,8 @@ SIGNATURES = {
     "rgbd_dv_workspace_bytes": (c_size, [ctypes.POINTER(DvParams)]),
     "rgbd_dv_compute_proj_idcs": (c_int, [ctypes.POINTER(DvParams), c_void, c_void, c_void, ctypes.POINTER(c_int),
                                           c_void, c_size, c_void]),
+    "rgbd_dv_compute_proj_idcs_g2w": (c_int, [ctypes.POINTER(DvParams), c_void, c_void, c_void, c_void, ctypes.POINTER(c_int),
+                                              c_void, c_size, c_void]),
     "rgbd_dv_trilinear_fwd": (c_int, [c_void, c_void, c_void, c_int, c_int, c_int, ctypes.POINTER(DvParams), c_void,
                                       c_void]),
     "rgbd_dv_trilinear_bwd": (c_int, [c_void, c_void, c_void, c_int, c_int, c_int, ctypes.POINTER(DvParams), c_void,

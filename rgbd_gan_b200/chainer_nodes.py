@@ -538,9 +538,6 @@ class ProjectionHelper:
         """projection.py:48-105 -> (lin_ind_frustrum int32 (M,), voxel_coords fp32 (3,M)) or None"""
         xp = self.xp
         cam = np.asarray(as_numpy(cam2world), dtype="float32")
-        if grid2world is not None:
-            # :53-54,:82-84: world2grid . (cam2world . p); the 4x4 . 4x4 product is folded on the host
-            cam = np.dot(np.linalg.inv(as_numpy(grid2world)), cam).astype("float32")
         cam = xp.asarray(np.ascontiguousarray(cam.reshape(16)), dtype="float32")
         P = self.params()
         n = P.W * P.H * P.D
@@ -550,8 +547,15 @@ class ProjectionHelper:
         if self._ws is None or self._ws.size < nbytes:
             self._ws = xp.empty(int(nbytes), dtype="uint8")
         M = ctypes.c_int(0)
-        self._lib.call("rgbd_dv_compute_proj_idcs", ctypes.byref(P), _ptr(cam), _ptr(lin), _ptr(vc), ctypes.byref(M),
-                       _ptr(self._ws), int(self._ws.size), _stream(xp))
+        if grid2world is not None:
+            # :53-54 world2grid = xp.linalg.inv(grid2world); :83-84 the second product per element runs on the device in the
+            # reference's order (rgbd_dv_compute_proj_idcs_g2w)
+            w2g = xp.asarray(np.ascontiguousarray(np.linalg.inv(as_numpy(grid2world)), dtype="float32").reshape(16), dtype="float32")
+            self._lib.call("rgbd_dv_compute_proj_idcs_g2w", ctypes.byref(P), _ptr(cam), _ptr(w2g), _ptr(lin), _ptr(vc),
+                           ctypes.byref(M), _ptr(self._ws), int(self._ws.size), _stream(xp))
+        else:
+            self._lib.call("rgbd_dv_compute_proj_idcs", ctypes.byref(P), _ptr(cam), _ptr(lin), _ptr(vc), ctypes.byref(M),
+                           _ptr(self._ws), int(self._ws.size), _stream(xp))
         if M.value == 0:
             print('error: nothing in frustum bounds')   # :98-100
             return None

@@ -55,6 +55,55 @@ __device__ __forceinline__ bool dv_coords(const rgbd_dv_params &P, const Cam &T,
     return dv_coords_at(P, T, d, l - d * WH, vc);                     // :65-66
 }
 
+// compute_proj_idcs with the optional grid2world argument (projection.py:53-54, :83-84): grid_coords = world2grid .
+// (cam2world . coords) -- two sgemm products with K = 4, all four rows of the first feed the second
+struct Cam2 { float t[16]; float g[12]; };
+
+__device__ __forceinline__ Cam2 load_cam2(const float *__restrict__ cam2world, const float *__restrict__ world2grid)
+{
+    Cam2 c;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c.t[k] = __ldg(cam2world + k);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) c.g[k] = __ldg(world2grid + k);
+    return c;
+}
+
+__device__ __forceinline__ bool dv_coords_g2w(const rgbd_dv_params &P, const Cam2 &T, int l, float vc[3])
+{
+    const int WH = P.W * P.H;
+    const int d = l / WH, tmp = l - d * WH;
+    const float yrow = (float)((double)tmp / (double)P.W);
+    const float xcol = (float)(tmp % P.W);
+    float zc = __fmul_rn((float)d, P.voxel_size);
+    zc = __fadd_rn(zc, P.near_plane);
+    float xc = __fdiv_rn(__fsub_rn(xcol, P.cx), P.fx);
+    float yc = __fdiv_rn(__fsub_rn(yrow, P.cy), P.fy);
+    xc = __fmul_rn(xc, zc);
+    yc = __fmul_rn(yc, zc);
+    float gc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        float g = __fmul_rn(T.t[4 * r], xc);
+        g = __fmaf_rn(T.t[4 * r + 1], yc, g);
+        g = __fmaf_rn(T.t[4 * r + 2], zc, g);
+        gc[r] = __fmaf_rn(T.t[4 * r + 3], 1.0f, g);
+    }
+    bool keep = true;
+    const float half = (float)P.G / 2.0f, Gf = (float)P.G;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float g = __fmul_rn(T.g[4 * r], gc[0]);
+        g = __fmaf_rn(T.g[4 * r + 1], gc[1], g);
+        g = __fmaf_rn(T.g[4 * r + 2], gc[2], g);
+        g = __fmaf_rn(T.g[4 * r + 3], gc[3], g);
+        const float v = __fadd_rn(__fdiv_rn(g, P.voxel_size), half);
+        vc[r] = v;
+        keep = keep && (v >= 0.0f) && (v < Gf);
+    }
+    return keep;
+}
+
 struct Taps {
     int off[8];         // element offsets into one (G,G,G) feature brick, corner order of deepvoxel.py:416-423
     float ax[8], ay[8], az[8];
@@ -420,13 +469,15 @@ k_dv_trilinear_bwd(const float *__restrict__ g_frustum, const int32_t *__restric
 
 // ---------------------------------------------------------------- compute_proj_idcs (ordered compaction)
 __global__ void __launch_bounds__(kThreads)
-k_dv_count(const rgbd_dv_params P, const float *__restrict__ cam2world, int *__restrict__ block_counts)
+k_dv_count(const rgbd_dv_params P, const float *__restrict__ cam2world, const float *__restrict__ world2grid,
+           int *__restrict__ block_counts)
 {
     const int n = P.W * P.H * P.D;
     const int l = blockIdx.x * kThreads + threadIdx.x;
-    const Cam T = load_cam(cam2world);
     float vc[3];
-    const bool keep = (l < n) && dv_coords(P, T, l, vc);
+    bool keep;
+    if (world2grid) keep = (l < n) && dv_coords_g2w(P, load_cam2(cam2world, world2grid), l, vc);
+    else keep = (l < n) && dv_coords(P, load_cam(cam2world), l, vc);
     const int cnt = __syncthreads_count(keep);
     if (threadIdx.x == 0) block_counts[blockIdx.x] = cnt;
 }
@@ -459,15 +510,16 @@ k_dv_scan(const int *__restrict__ block_counts, int nblocks, int *__restrict__ b
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_dv_compact(const rgbd_dv_params P, const float *__restrict__ cam2world, const int *__restrict__ block_offsets,
-             int32_t *__restrict__ lin_ind, float *__restrict__ voxel_coords, int ld)
+k_dv_compact(const rgbd_dv_params P, const float *__restrict__ cam2world, const float *__restrict__ world2grid,
+             const int *__restrict__ block_offsets, int32_t *__restrict__ lin_ind, float *__restrict__ voxel_coords, int ld)
 {
     __shared__ int warp_base[kThreads / 32];
     const int n = P.W * P.H * P.D;
     const int l = blockIdx.x * kThreads + threadIdx.x;
-    const Cam T = load_cam(cam2world);
     float vc[3];
-    const bool keep = (l < n) && dv_coords(P, T, l, vc);
+    bool keep;
+    if (world2grid) keep = (l < n) && dv_coords_g2w(P, load_cam2(cam2world, world2grid), l, vc);
+    else keep = (l < n) && dv_coords(P, load_cam(cam2world), l, vc);
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (lane == 0) warp_base[wid] = __popc(bal);
@@ -943,9 +995,28 @@ RGBD_API size_t rgbd_dv_workspace_bytes(const rgbd_dv_params *p)
     return (2 * nblocks + 64) * sizeof(int);
 }
 
+static int dv_compute_proj_idcs_impl(const rgbd_dv_params *p, const float *cam2world, const float *world2grid,
+                                     int32_t *lin_ind, float *voxel_coords, int *M_host, void *workspace,
+                                     size_t workspace_bytes, void *stream);
+
 RGBD_API int rgbd_dv_compute_proj_idcs(const rgbd_dv_params *p, const float *cam2world, int32_t *lin_ind,
                               float *voxel_coords, int *M_host, void *workspace, size_t workspace_bytes,
                               void *stream)
+{
+    return dv_compute_proj_idcs_impl(p, cam2world, nullptr, lin_ind, voxel_coords, M_host, workspace, workspace_bytes, stream);
+}
+
+RGBD_API int rgbd_dv_compute_proj_idcs_g2w(const rgbd_dv_params *p, const float *cam2world, const float *world2grid,
+                                           int32_t *lin_ind, float *voxel_coords, int *M_host, void *workspace,
+                                           size_t workspace_bytes, void *stream)
+{
+    if (!world2grid) { set_error("rgbd_dv_compute_proj_idcs_g2w: null world2grid"); return RGBD_E_ARG; }
+    return dv_compute_proj_idcs_impl(p, cam2world, world2grid, lin_ind, voxel_coords, M_host, workspace, workspace_bytes, stream);
+}
+
+static int dv_compute_proj_idcs_impl(const rgbd_dv_params *p, const float *cam2world, const float *world2grid,
+                                     int32_t *lin_ind, float *voxel_coords, int *M_host, void *workspace,
+                                     size_t workspace_bytes, void *stream)
 {
     if (!dv_ok(p) || !cam2world || !lin_ind || !voxel_coords || !M_host) {
         set_error("rgbd_dv_compute_proj_idcs: null pointer or bad params");
@@ -959,9 +1030,9 @@ RGBD_API int rgbd_dv_compute_proj_idcs(const rgbd_dv_params *p, const float *cam
     const int n = p->W * p->H * p->D;
     const int nblocks = (n + kThreads - 1) / kThreads;
     int *counts = (int *)workspace, *offsets = counts + nblocks, *total = offsets + nblocks;
-    k_dv_count<<<nblocks, kThreads, 0, st>>>(*p, cam2world, counts);
+    k_dv_count<<<nblocks, kThreads, 0, st>>>(*p, cam2world, world2grid, counts);
     k_dv_scan<<<1, 1024, 0, st>>>(counts, nblocks, offsets, total);
-    k_dv_compact<<<nblocks, kThreads, 0, st>>>(*p, cam2world, offsets, lin_ind, voxel_coords, n);
+    k_dv_compact<<<nblocks, kThreads, 0, st>>>(*p, cam2world, world2grid, offsets, lin_ind, voxel_coords, n);
     count_launch(3);
     int rc = check_launch("rgbd_dv_compute_proj_idcs");
     if (rc) return rc;

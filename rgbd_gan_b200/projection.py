@@ -90,9 +90,6 @@ class ProjectionHelper:
 
     def compute_proj_idcs(self, cam2world, grid2world=None):
         """projection.py:48-105 -> (lin_ind_frustrum int32 (M,), voxel_coords fp32 (3,M)) or None."""
-        if grid2world is not None:
-            # world2grid is a constant 4x4: fold it into the camera matrix on the host (:53-54,:83-84)
-            cam2world = np.dot(np.linalg.inv(_as_numpy(grid2world)), _as_numpy(cam2world)).astype("float32")
         dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
         if isinstance(cam2world, torch.Tensor) and cam2world.is_cuda:
             dev = cam2world.device
@@ -105,8 +102,15 @@ class ProjectionHelper:
             self._ws = torch.empty(_lib.load().rgbd_dv_workspace_bytes(ctypes.byref(P)), dtype=torch.uint8, device=dev)
         M = ctypes.c_int(0)
         with torch.cuda.device(dev):
-            _lib.call("rgbd_dv_compute_proj_idcs", ctypes.byref(P), _ptr(cam), _ptr(lin), _ptr(vc), ctypes.byref(M),
-                      _ptr(self._ws), self._ws.numel(), _stream())
+            if grid2world is not None:
+                # :53-54 world2grid = xp.linalg.inv(grid2world); :83-84 a SECOND product per element, evaluated on the device
+                # in the reference's order (folding the two matrices on the host changes the last bits of the coordinates)
+                w2g = torch.from_numpy(np.ascontiguousarray(np.linalg.inv(_as_numpy(grid2world)), dtype=np.float32)).to(dev)
+                _lib.call("rgbd_dv_compute_proj_idcs_g2w", ctypes.byref(P), _ptr(cam), _ptr(w2g.reshape(16)), _ptr(lin), _ptr(vc),
+                          ctypes.byref(M), _ptr(self._ws), self._ws.numel(), _stream())
+            else:
+                _lib.call("rgbd_dv_compute_proj_idcs", ctypes.byref(P), _ptr(cam), _ptr(lin), _ptr(vc), ctypes.byref(M),
+                          _ptr(self._ws), self._ws.numel(), _stream())
         if M.value == 0:
             print('error: nothing in frustum bounds')   # :98-100
             return None

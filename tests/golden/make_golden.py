@@ -218,7 +218,7 @@ def dv_helper(pj, G, img, scale=0.5):
     return h, D, voxel_size, near_plane
 
 
-def dv_case(pj, dv, get_cam, Prior, name, seed, G, img, F, nsamp):
+def dv_case(pj, dv, get_cam, Prior, name, seed, G, img, F, nsamp, g2w=False):
     np.random.seed(seed)
     h, D, voxel_size, near_plane = dv_helper(pj, G, img)
     thetas = Prior(Cfg(**DV_CAR)).sample(2 * ((nsamp + 1) // 2))[:nsamp]
@@ -238,6 +238,27 @@ def dv_case(pj, dv, get_cam, Prior, name, seed, G, img, F, nsamp):
         d["frustum_%d" % i] = out.array
         d["g_grid_%d" % i] = gv.grad
         print("%-22s sample %d: M=%d of %d" % (name, i, lin_ind.size, D * img * img))
+    if g2w:
+        # the optional second argument of compute_proj_idcs (projection.py:48,53-54,83-84; no caller in the reference):
+        # a rigid motion + scale of the grid, drawn from its own generator so that the rest of the file is unchanged
+        rs = np.random.RandomState(seed + 1000)
+        ang = rs.uniform(-0.4, 0.4, size=3)
+        Rg = np.eye(3)
+        for ax, a in enumerate(ang):
+            c_, s_ = np.cos(a), np.sin(a)
+            R1 = np.eye(3)
+            i0, i1 = (ax + 1) % 3, (ax + 2) % 3
+            R1[i0, i0], R1[i0, i1], R1[i1, i0], R1[i1, i1] = c_, -s_, s_, c_
+            Rg = R1 @ Rg
+        g2w_m = np.eye(4)
+        g2w_m[:3, :3] = Rg * 1.07
+        g2w_m[:3, 3] = rs.uniform(-0.05, 0.05, size=3)
+        g2w_m = g2w_m.astype("float32")
+        lin_ind, vc = h.compute_proj_idcs(cam[0], g2w_m)
+        d["grid2world"] = g2w_m
+        d["lin_ind_g2w_0"] = lin_ind
+        d["voxel_coords_g2w_0"] = vc
+        print("%-22s grid2world: M=%d" % (name, lin_ind.size))
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
 
 
@@ -342,7 +363,7 @@ def main():
     hinge_case(lf, get_cam, Prior, "hinge_car", 13, B=3, S=32, depth="smooth", pose=CAR, depth_min=0.6, lambda_depth=10)
     # DeepVoxels projection: scaled-down geometry with several features, and the
     # production geometry (deepvoxels_generator.py:229-253) with one feature
-    dv_case(pj, dv, get_cam, Prior, "dv_g16_f3", 10, G=16, img=32, F=3, nsamp=2)
+    dv_case(pj, dv, get_cam, Prior, "dv_g16_f3", 10, G=16, img=32, F=3, nsamp=2, g2w=True)
     dv_case(pj, dv, get_cam, Prior, "dv_g32_f1", 11, G=32, img=64, F=1, nsamp=1)
     # next row: DeepVoxels render tail with the accumulative occlusion module
     render_case(pj, dv, get_cam, Prior, "render_g16", 20, G=16, img=32, F=32, nsamp=2)

@@ -122,3 +122,18 @@ def test_empty_frustum_returns_zero_count():
     cam[:3, 3] += 100.0
     M, _, _ = _proj_idcs(P, cam)
     assert M == 0
+
+
+def test_grid2world_argument_bit_exact():
+    """compute_proj_idcs(cam2world, grid2world) (projection.py:48,53-54,83-84) on the device in the reference's order"""
+    from rgbd_gan_b200.projection import ProjectionHelper
+    g = load_golden("dv_g16_f3")
+    G, img, D = int(g["G"]), int(g["img"]), int(g["D"])
+    h = ProjectionHelper(g["intrinsic"], g["intrinsic"], [img, img], [img, img], 0., 1., [G] * 3, float(g["voxel_size"]),
+                         float(g["near_plane"]), D, verbose=False)
+    lin, vc = h.compute_proj_idcs(g["cam"][0], g["grid2world"])
+    np.testing.assert_array_equal(lin.cpu().numpy(), g["lin_ind_g2w_0"])
+    np.testing.assert_array_equal(vc.cpu().numpy(), g["voxel_coords_g2w_0"])
+    lin0, vc0 = h.compute_proj_idcs(g["cam"][0])                 # the plain call is untouched
+    np.testing.assert_array_equal(lin0.cpu().numpy(), g["lin_ind_0"])
+    np.testing.assert_array_equal(vc0.cpu().numpy(), g["voxel_coords_0"])

@@ -157,6 +157,25 @@ def test_deepvoxels_oracle_matches_reference(name, oracle_mod):
         assert_grad_close(gfused[i], g["g_grid_%d" % i][0])
 
 
+def test_deepvoxels_grid2world_argument(oracle_mod):
+    """the optional second argument of compute_proj_idcs (projection.py:48,53-54,83-84): two K = 4 products per element;
+    both restatements reproduce the reference's lin_ind / voxel_coords bit for bit, the folded single product does not"""
+    from oracle import numpy_port as npp
+    g = load_golden("dv_g16_f3")
+    G, img, D = int(g["G"]), int(g["img"]), int(g["D"])
+    P = oracle_mod.dv_params(img, img, D, G, g["intrinsic"], float(g["voxel_size"]), float(g["near_plane"]))
+    lin, vc = oracle_mod.dv_compute_proj_idcs(P, g["cam"][0], g["grid2world"])
+    np.testing.assert_array_equal(lin, g["lin_ind_g2w_0"])
+    np.testing.assert_array_equal(vc, g["voxel_coords_g2w_0"])
+    h = npp.ProjectionHelperNP(g["intrinsic"], [img, img], [G] * 3, float(g["voxel_size"]), float(g["near_plane"]), D)
+    lin2, vc2 = h.compute_proj_idcs(g["cam"][0], g["grid2world"])
+    np.testing.assert_array_equal(lin2, g["lin_ind_g2w_0"])
+    np.testing.assert_array_equal(vc2, g["voxel_coords_g2w_0"])
+    folded = np.dot(np.linalg.inv(g["grid2world"]), g["cam"][0]).astype("float32")
+    _, vc3 = oracle_mod.dv_compute_proj_idcs(P, folded)
+    assert vc3.shape != vc.shape or not np.array_equal(vc3, vc)
+
+
 def test_dv_empty_frustum(oracle_mod):
     """camera far outside the grid: the reference prints an error and returns None (projection.py:98-100)"""
     g = load_golden("dv_g16_f3")
