@@ -28,7 +28,8 @@ def _proj_idcs(P, cam):
     vc = torch.empty((3, n), device=DEV)
     ws = torch.empty(_lib.load().rgbd_dv_workspace_bytes(ctypes.byref(P)), dtype=torch.uint8, device=DEV)
     M = ctypes.c_int(-1)
-    _lib.call("rgbd_dv_compute_proj_idcs", ctypes.byref(P), p(dev(cam.reshape(16))), p(lin), p(vc), ctypes.byref(M),
+    d_cam = dev(cam.reshape(16))
+    _lib.call("rgbd_dv_compute_proj_idcs", ctypes.byref(P), p(d_cam), p(lin), p(vc), ctypes.byref(M),
               p(ws), ws.numel(), stream())
     return M.value, lin, vc
 
@@ -100,14 +101,14 @@ def test_full_size_against_oracle(G, F, B, exact, oracle_mod, monkeypatch):
     n = img * img * D
     out = torch.empty((B, F, n), device=DEV)
     ws = torch.empty(_lib.load().rgbd_dv_project_workspace_bytes(ctypes.byref(P), B, F), dtype=torch.uint8, device=DEV)
-    _lib.call("rgbd_dv_project_fwd", ctypes.byref(P), p(dev(grid)), p(dev(cam.reshape(B, 16))), B, F, p(out), p(ws),
-              ws.numel(), stream())
+    d_grid, d_cam = dev(grid), dev(cam.reshape(B, 16))       # referenced until the end: raw pointers go to the library
+    _lib.call("rgbd_dv_project_fwd", ctypes.byref(P), p(d_grid), p(d_cam), B, F, p(out), p(ws), ws.numel(), stream())
     assert_frustum_close(out.cpu().numpy().reshape(ref.shape), ref, exact == "1")
     g_out = rng.normal(size=ref.shape).astype(np.float32)
     ref_g = oracle_mod.dv_project_bwd(P0, g_out, cam)
     gg = torch.empty((B, F, G ** 3), device=DEV)
-    _lib.call("rgbd_dv_project_bwd", ctypes.byref(P), p(dev(g_out)), p(dev(cam.reshape(B, 16))), B, F, p(gg), p(ws),
-              ws.numel(), stream())
+    d_gout = dev(g_out)
+    _lib.call("rgbd_dv_project_bwd", ctypes.byref(P), p(d_gout), p(d_cam), B, F, p(gg), p(ws), ws.numel(), stream())
     assert_grad_close(gg.cpu().numpy().reshape(ref_g.shape), ref_g)
     # adjointness <frustum(grid), g_out> == <grid, lift(g_out)> : a size-independent property of the pair
     lhs = float((ref.astype(np.float64) * g_out).sum())

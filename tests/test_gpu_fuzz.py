@@ -31,3 +31,20 @@ def test_random_cases_against_oracle(seed, oracle_mod, monkeypatch):
                 os.environ.pop(name, None)
             else:
                 os.environ[name] = val
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_random_deepvoxels_cases_against_oracle(seed, oracle_mod, monkeypatch):
+    """tools/fuzz_parity_dv.py: random grid / image sizes (incl. widths that are not powers of two), feature counts, poses,
+    grid2world, exact / folded mode: compute_proj_idcs bit-exact, fused projection and lift against the C oracle"""
+    import fuzz_parity_dv
+    saved = os.environ.get("RGBD_B200_DV_EXACT")
+    rng = np.random.default_rng(seed)
+    try:
+        for _ in range(10):
+            fuzz_parity_dv.run_case(fuzz_parity_dv.draw_case(rng), oracle_mod)
+    finally:
+        if saved is None:
+            os.environ.pop("RGBD_B200_DV_EXACT", None)
+        else:
+            os.environ["RGBD_B200_DV_EXACT"] = saved
