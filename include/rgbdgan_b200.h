@@ -186,8 +186,9 @@ RGBD_API int rgbd_consistency_rescale(float *g_img, float *g_img_rot, size_t n_e
 RGBD_API int rgbd_peer_comm_create(int rank, int world, void **comm_out, unsigned char *ipc_handle_out);
 RGBD_API int rgbd_peer_comm_connect(void *comm, const unsigned char *all_handles);
 RGBD_API int rgbd_peer_comm_destroy(void *comm);
-/* make `stream` wait for the most recent (deferred) loss exchange of this comm; after defer_loss == 2 calls: launch the
- * kernel that sums the latest call's published parts into its loss_parts */
+/* make `stream` wait for the most recent (deferred) loss exchange of this comm; after defer_loss == 2 calls: launch, ON
+ * `stream`, the kernel that sums the latest call's published parts into its loss_parts (`stream` must be the stream of
+ * those loss calls or ordered after them) */
 RGBD_API int rgbd_peer_comm_wait(void *comm, void *stream);
 /* Health of the exchange: every wait for a peer's flag inside the finalize kernel is bounded (2 s, env
  * RGBD_B200_PEER_TIMEOUT_MS); a wait that expires -- a rank died, or made a different sequence of loss calls --
