@@ -746,6 +746,49 @@ def render_bench(ctx_):
     return out
 
 
+def pose_pipeline_bench(a, ctx_):
+    """camera parameters -> cam2world -> warp constants for `pairs` pairs.  Device: ONE launch of
+    rgbd_pose_pipeline (sampling included), CUDA events over 200 calls.  Host: what a step pays when the thetas live on the
+    host -- the reference's NumPy chain (sampler, get_camera_matries, the pose algebra of LossFuncRotate.__call__) plus the
+    pinned upload of the 24 floats per pair, wall clock."""
+    import torch
+    from types import SimpleNamespace
+    from tools import synthetic as poses
+    from rgbd_gan_b200.host_math import intrinsics_for_size, pose_algebra
+    from rgbd_gan_b200.loss_functions import _PoseUploader
+    from rgbd_gan_b200.pose_pipeline import CameraParamPrior, PosePipeline
+    dev, B = ctx_["dev"], a.pairs
+    K, inv_K = intrinsics_for_size(None, a.size, first=True)
+    r = poses.FFHQ_RANGES
+    cfg = SimpleNamespace(x_rotate=r[0], y_rotate=r[1], z_rotate=r[2], x_translate=r[3], y_translate=r[4], z_translate=r[5],
+                          uniform_distribution=False)
+    pipe = PosePipeline(CameraParamPrior(cfg, dev, seed=1), K, inv_K)
+    for _ in range(10):
+        pipe.step(2 * B)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 200
+    e0.record()
+    for _ in range(n):
+        pipe.step(2 * B)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    dev_us = e0.elapsed_time(e1) * 1e3 / n
+    up, rng = _PoseUploader(), np.random.default_rng(0)
+    t0 = time.perf_counter()
+    m = 50
+    for _ in range(m):
+        cam = poses.cam2world(poses.sample_pose_pairs(B, r, False, rng))
+        M, c, Mi, ci = pose_algebra(K, inv_K, cam[:B], cam[B:])
+        up.upload(M, c, Mi, ci, dev)
+    torch.cuda.synchronize(dev)
+    host_us = (time.perf_counter() - t0) * 1e6 / m
+    return {"pairs": B, "device_one_launch_us": dev_us, "host_numpy_chain_plus_upload_us": host_us,
+            "note": "device: rgbd_pose_pipeline (Philox sampling + get_camera_matries + pose algebra; the figure is the issue rate of "
+                    "the Python glue -- three output allocations + one ctypes call -- the kernel itself runs a few us); host: NumPy sampler + get_camera_matries + pose_algebra + pinned H2D of 24 floats per "
+                    "pair; bit-exactness of the device path against the host path: tests/test_gpu_poses.py"}
+
+
 def feature_consistency_bench(a, ctx_):
     """the feature-space consistency loss of updater.py:345-354 (norm l2, C = 256 features +
     1 depth at 32x32, yml batch 32 -> 16 pairs); runs through the generic-C kernels (not tuned)."""
@@ -863,6 +906,7 @@ def main():
         line["deepvoxels"] = deepvoxels_bench(ctx_)
         line["deepvoxels_render_fused"] = render_bench(ctx_)
         line["feature_consistency_c257"] = feature_consistency_bench(a, ctx_)
+        line["pose_pipeline"] = pose_pipeline_bench(a, ctx_)
     if not a.no_cpu:
         line["cpu_baseline"] = cpu_baseline_leg(a)
     emit(line)
