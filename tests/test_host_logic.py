@@ -190,3 +190,98 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+# ---- the rounding orders csrc/poses.cu hard-codes, restated in NumPy (fp32 products are exact in fp64, so
+# float32(float64(a) * float64(b) + float64(c)) is a single-rounding fma except for rare double roundings) and checked against
+# this host's NumPy / BLAS on every golden case.  Pins the claim "the device pose pipeline reproduces the reference's CPU
+# path product by product" on the CPU side too; skipped on a host whose BLAS uses other kernels (the GPU tests compare
+# the kernel with the golden vectors directly and do not depend on the host).
+def _fma(a, b, c):
+    return np.float32(np.float64(a) * np.float64(b) + np.float64(c))
+
+
+def _chain(A, Bm):
+    n, k = A.shape
+    out = np.zeros((n, Bm.shape[1]), np.float32)
+    for i in range(n):
+        for j in range(Bm.shape[1]):
+            s = np.float32(A[i, 0] * Bm[0, j])
+            for l in range(1, k):
+                s = _fma(A[i, l], Bm[l, j], s)
+            out[i, j] = s
+    return out
+
+
+def _matvec_blas(A, v):
+    out = np.zeros((3, 1), np.float32)
+    for i in range(2):
+        s = np.float32(A[i, 0] * v[0, 0])
+        s = np.float32(s + np.float32(A[i, 1] * v[1, 0]))
+        out[i, 0] = np.float32(s + np.float32(A[i, 2] * v[2, 0]))
+    out[2, 0] = _fma(A[2, 2], v[2, 0], _fma(A[2, 0], v[0, 0], np.float32(A[2, 1] * v[1, 0])))
+    return out
+
+
+def _device_order_pose_algebra(K, inv_K, th, thr):
+    R1, R2 = th[:3, :3], thr[:3, :3]
+    R = _chain(np.ascontiguousarray(R2.T), R1)
+    dt = (thr[:3, 3:] - th[:3, 3:]).astype(np.float32)
+    t = _chain(np.ascontiguousarray(R1.T), dt)
+    KR = _chain(K, R)
+    return _chain(KR, inv_K), _matvec_blas(KR, t), _chain(_chain(K, np.ascontiguousarray(R.T)), inv_K), -_matvec_blas(K, t)
+
+
+def _host_blas_matches_golden_host():
+    rng = np.random.default_rng(0)
+    A, v = rng.normal(size=(5, 3, 3)).astype(np.float32), rng.normal(size=(5, 3, 1)).astype(np.float32)
+    Bm = rng.normal(size=(5, 3, 3)).astype(np.float32)
+    return all(np.array_equal(np.matmul(A, v)[b], _matvec_blas(A[b], v[b])) and
+               np.array_equal(np.matmul(A, Bm)[b], _chain(A[b], Bm[b])) for b in range(5))
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_device_pose_orders_restated_in_numpy(name):
+    from rgbd_gan_b200.host_math import intrinsics_for_size, pose_algebra
+    if not _host_blas_matches_golden_host():
+        pytest.skip("this host's BLAS evaluates small products in another order than the golden host's")
+    g = load_golden(name)
+    o = case_options(g)
+    B = o["B"]
+    K, inv_K = intrinsics_for_size(o["K"], o["S"], first=True)
+    M, c, Mi, ci = pose_algebra(K, inv_K, g["cam"][:B], g["cam"][B:])
+    for b in range(B):
+        m, cc, mi, cci = _device_order_pose_algebra(K, inv_K, g["cam"][b], g["cam"][B + b])
+        np.testing.assert_array_equal(m, M[b])
+        np.testing.assert_array_equal(cc, c[b])
+        np.testing.assert_array_equal(mi, Mi[b])
+        np.testing.assert_array_equal(cci, ci[b])
+
+
+def test_device_camera_matrix_order_restated_in_numpy():
+    """get_camera_matries (updater.py:45-60): three 4x4 products as fma chains reproduce every golden cam2world matrix when
+    fed NumPy's own cos / sin"""
+    import glob
+    import os
+    from conftest import GOLDEN
+    if not _host_blas_matches_golden_host():
+        pytest.skip("other BLAS order on this host")
+    for path in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
+        g = np.load(path)
+        if "thetas" not in g.files:
+            continue
+        th = g["thetas"]
+        if not np.array_equal(npp.get_camera_matries(th), g["cam"]):      # this host's cos / sin differ from the golden host's
+            continue
+        for b in range(min(len(th), 2)):
+            mat = np.zeros((4, 4), np.float32)
+            mat[range(4), range(4)] = [1, 1, -1, 1]
+            mat[2, 3] = 1
+            for i in (0, 1, 2):
+                a1, a2 = (i + 1) % 3, (i + 2) % 3
+                rot = np.eye(4, dtype=np.float32)
+                cs, sn = np.cos(th[b:b + 1, i])[0], np.sin(th[b:b + 1, i])[0]
+                rot[a1, a1], rot[a1, a2], rot[a2, a1], rot[a2, a2] = cs, -sn, sn, cs
+                mat = _chain(rot, mat)
+            mat[:3, 3] = mat[:3, 3] + th[b, 3:]
+            np.testing.assert_array_equal(mat, g["cam"][b])
