@@ -217,6 +217,39 @@ class OracleBackedLib:
                 _view(dst, sh)[...] = self.oracle.dv_project_fwd(P0, _view(src, (B, F, G, G, G)), _view(cam, (B, 4, 4)))
             else:
                 _view(dst, (B, F, G, G, G))[...] = self.oracle.dv_project_bwd(P0, _view(src, sh), _view(cam, (B, 4, 4)))
+        elif name == "rgbd_dv_compute_proj_idcs_g2w":
+            P, cam, w2g, lin, vc, M, ws, wsb, _ = a
+            P = P._obj
+            n = P.W * P.H * P.D
+            g2w = np.linalg.inv(_view(w2g, (4, 4)).astype(np.float64)).astype(np.float32)
+            r = self.oracle.dv_compute_proj_idcs(self._dvp(P), _view(cam, (4, 4)), np.linalg.inv(np.linalg.inv(g2w)))
+            M._obj.value = 0 if r is None else r[0].size
+            if r is not None:
+                _view(lin, (n,), ctypes.c_int32)[:r[0].size] = r[0]
+                _view(vc, (3, n))[:, :r[0].size] = r[1]
+        elif name == "rgbd_pose_algebra":
+            from rgbd_gan_b200.host_math import pose_algebra
+            th, thr, B, K, iK, M, c, Mi, ci, _ = a
+            Kn, iKn = np.array(list(K), np.float32).reshape(3, 3), np.array(list(iK), np.float32).reshape(3, 3)
+            outs = pose_algebra(Kn, iKn, _view(th, (B, 4, 4)), _view(thr, (B, 4, 4)))
+            for ptr, o in zip((M, c, Mi, ci), outs):
+                _view(ptr, o.shape)[...] = o
+        elif name == "rgbd_pose_camera_matrices":
+            from oracle import numpy_port as npp_
+            th, cs, n, order, cam, _ = a
+            _view(cam, (n, 4, 4))[...] = npp_.get_camera_matries(_view(th, (n, 6)), tuple(order))
+        elif name == "rgbd_pose_sample":
+            prior, B, draws, seed, step, out, _ = a
+            pr = prior._obj
+            d = _view(draws, (B, 15), ctypes.c_double)
+            rng_, uni = np.array(list(pr.camera_param_range)), bool(pr.uniform_distribution)
+            u, e, sign = d[:, :6].copy(), d[:, 6:12].copy(), d[:, 12:] * 2 - 1
+            lim = np.clip(1 / (rng_[:3] + 1e-8), 0, 1)
+            e[:, :3] = e[:, :3] * (sign if uni else (sign * (rng_[:3] == 3.1415) + np.abs(sign) * (rng_[:3] != 3.1415))) * lim
+            t2 = -e * np.sign(u) + u
+            if uni:
+                t2 = t2 * (-1 <= t2) * (t2 <= 1) + (-2 - t2) * (t2 < -1) + (2 - t2) * (t2 > 1)
+            _view(out, (2 * B, 6))[...] = (np.concatenate([u, t2], axis=0) * rng_[None]).astype("float32")
         elif name == "rgbd_depth_head_fwd":
             from oracle import numpy_port as npp_
             h, B, C, H, W, out, _ = a
@@ -430,3 +463,56 @@ def test_chainer_depth_head_node(nodes, oracle_mod):
     np.testing.assert_array_equal(np.asarray(out.array), g["out"])
     np.testing.assert_allclose(np.asarray(h.grad), g["g_h"], rtol=1e-6, atol=1e-12)
     assert lib.calls == ["rgbd_depth_head_fwd", "rgbd_depth_head_bwd"]
+
+
+class DevArr:
+    """a device array as the glue sees it when it is NOT a numpy array: `.data.ptr`, shape, dtype, slicing, `get()`"""
+
+    def __init__(self, a):
+        self.a = np.ascontiguousarray(a)
+
+    data = property(lambda s: _Ptr(s.a))
+    shape = property(lambda s: s.a.shape)
+    dtype = property(lambda s: s.a.dtype)
+    ndim = property(lambda s: s.a.ndim)
+
+    def __array__(self, dtype=None, copy=None):
+        return self.a if dtype is None else self.a.astype(dtype)
+
+    def __getitem__(self, k):
+        return DevArr(self.a[k])
+
+    def get(self):
+        return self.a
+
+
+def test_device_thetas_take_the_pose_kernel(nodes, oracle_mod):
+    """SURVEY 8f rank 4 on the Chainer surface: thetas that are DEVICE arrays go through rgbd_pose_algebra (no .get()); host
+    thetas keep the NumPy path; get_camera_matries / CameraParamPrior marshal their arguments as the header says"""
+    g = load_golden("loss_cfg0_l1_occ")
+    o = case_options(g)
+    B = o["B"]
+    lib = OracleBackedLib(oracle_mod)
+    f = nodes.LossFuncRotate(FakeXP(), lambda_geometric=o["lam"], lib=lib)
+    img, img_rot = chainer_shim.Variable(_wrap(g["x"][:B])), chainer_shim.Variable(_wrap(g["x"][B:]))
+    cam = DevArr(g["cam"])
+    loss, zp = f(img, cam[:B], img_rot, cam[B:], occlusion_aware=o["occ"])
+    assert lib.calls[0] == "rgbd_pose_algebra" and "rgbd_consistency_fwd" in lib.calls
+    np.testing.assert_array_equal(np.asarray(zp.array), g["new_zp_cat"])
+    assert abs(float(loss.array) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    lib.calls.clear()
+    f(img, g["cam"][:B], img_rot, g["cam"][B:], occlusion_aware=o["occ"])              # host thetas: no pose kernel
+    assert "rgbd_pose_algebra" not in lib.calls
+    got = nodes.get_camera_matries(DevArr(g["thetas"]), xp=FakeXP(), lib=lib)
+    np.testing.assert_array_equal(np.asarray(got), g["cam"])
+    cfg = types.SimpleNamespace(x_rotate=0.3054, y_rotate=1.0472, z_rotate=0, x_translate=0, y_translate=0, z_translate=0,
+                                uniform_distribution=False)
+    from oracle import numpy_port as npp
+    np.random.seed(9)
+    u, e, s = np.random.uniform(-1, 1, (B, 6)), np.random.uniform(0, 0.5, (B, 6)), np.random.choice(2, (B, 3))
+    np.random.seed(9)
+    want = npp.sample_camera_prior(2 * B, npp.FFHQ_RANGES, False)
+    pr = nodes.CameraParamPrior(cfg, xp=FakeXP(), lib=lib)
+    got = pr.sample(2 * B, draws=np.concatenate([u, e, s.astype(np.float64)], 1))
+    np.testing.assert_array_equal(np.asarray(got), want)
+    assert pr.step == 1 and lib.calls[-1] == "rgbd_pose_sample"
